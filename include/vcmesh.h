@@ -1,0 +1,165 @@
+/* libvcmesh.so — the vc-conv / vd-pool / vd-unpool hot path of VCMeshConv as
+ * hand-written sm_100a CUDA kernels behind a plain C ABI.
+ *
+ * The reference has no FFI layer: its hot path is the ATen op sequence inside
+ * LASMConvssw.forward (GraphAutoEncoder/graphVAESSW.py:97-163) and the autograd
+ * mirror of it. Each entry point below replaces one slice of that sequence;
+ * the Python layer in vcmeshconv_b200/ (same nn.Module API as the reference)
+ * binds them with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer argument of a compute call is a DEVICE pointer to
+ *     contiguous row-major fp32 (or int32 where stated) on the current device;
+ *   - every compute call takes the cudaStream_t it must enqueue on (as
+ *     void*), is asynchronous, allocates nothing and holds no global mutable
+ *     state (CUDA-graph capturable); the caller owns all buffers;
+ *   - return value: 0 = ok, otherwise a VCM_E* code below or a cudaError_t
+ *     (>0); vcm_last_error() returns the message of the last failure on the
+ *     calling thread. Nothing throws, nothing exits;
+ *   - there is NO CPU fallback: host pointers are rejected.
+ *
+ * Shapes:  B batch, P_in / P_out vertex counts, N padded neighbour count,
+ *          M number of bases, I / O channels, R = B*P_out rows, K = M*I.
+ *   x [B,P_in,I]   A [P_out,N,M]   z [B,P_out,M,I] = [R,K]
+ *   W [M,O,I] (the reference's `weights` [M, O*I], native layout)
+ *   y / out [B,P_out,O]   bias [P_out,O] or [O]
+ */
+#ifndef VCMESH_H
+#define VCMESH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VCM_API __attribute__((visibility("default")))
+#else
+#define VCM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    VCM_OK = 0,
+    VCM_EINVAL = -1,      /* bad argument (shape, null pointer, host pointer) */
+    VCM_EUNSUPPORTED = -2,/* valid request this build has no kernel for */
+    VCM_ENOMEM = -3
+};
+
+/* GEMM arithmetic for the basis GEMMs (vcm_basis_*):
+ *   VCM_PREC_FP32   fp32 FMA on CUDA cores: the reference's own arithmetic
+ *   VCM_PREC_TF32   tcgen05 kind::tf32, fp32 accumulate in TMEM (1 pass)
+ *   VCM_PREC_TF32X3 tcgen05, 3-pass hi/lo split: fp32-grade result on tensor cores
+ * Shapes the tensor-core kernels do not cover fall back to VCM_PREC_FP32
+ * kernels (still CUDA, never the CPU). */
+enum { VCM_PREC_FP32 = 0, VCM_PREC_TF32 = 1, VCM_PREC_TF32X3 = 2 };
+
+VCM_API const char *vcm_last_error(void);
+VCM_API int vcm_version(void);
+/* 1 when a tcgen05 kernel exists for this (rows, K, O) and precision. */
+VCM_API int vcm_basis_uses_tensor_cores(int64_t rows, int M, int I, int O, int precision);
+
+/* ---------------------------------------------------------------- tables --
+ * Immutable per-layer connectivity on the device. Replaces the parsing done in
+ * LASMConvssw.__init__ (graphVAESSW.py:44-57) and the per-call sentinel mask
+ * (graphVAESSW.py:111-118).
+ *
+ * table_host: HOST int32 [P_out, cols], cols = 1 + 2N, rows as written by
+ * GraphSampling (meshCNN.h:54-92): [cnt, id0, hop0, id1, hop1, ...], padding
+ * id == P_in. Derived device tables:
+ *   idx      int32 [P_out, N]   neighbour ids (sentinel P_in kept as is)
+ *   last     int32 [P_out]      1 + position of the last non-sentinel entry
+ *   perm     int32 [P_out]      output vertices sorted by `last` descending
+ *                               (stable) = degree-bucketed processing order
+ *   rev_ptr  int32 [P_in + 1]   CSR row pointers of the transposed graph
+ *   rev_slot int32 [nnz]        for input vertex q the slots p*N+n with
+ *                               idx[p,n] == q, ascending (deterministic dX)
+ */
+typedef struct vcm_tables vcm_tables;
+
+typedef struct vcm_tables_info {
+    int32_t p_in, p_out, n_max;
+    int32_t max_last;   /* max over rows of `last` */
+    int64_t nnz;        /* non-sentinel entries */
+    int32_t max_rev;    /* max in-degree of the transposed graph */
+    int32_t device;
+} vcm_tables_info;
+
+enum { VCM_TAB_IDX = 0, VCM_TAB_LAST = 1, VCM_TAB_PERM = 2, VCM_TAB_REV_PTR = 3, VCM_TAB_REV_SLOT = 4 };
+
+VCM_API int vcm_tables_create(const int32_t *table_host, int p_out, int cols, int p_in, vcm_tables **out);
+VCM_API void vcm_tables_destroy(vcm_tables *t);
+VCM_API int vcm_tables_get_info(const vcm_tables *t, vcm_tables_info *info);
+/* Copies one derived table back to the host (tests: bit-exactness). */
+VCM_API int vcm_tables_export(const vcm_tables *t, int which, int32_t *dst_host, size_t capacity_elems);
+/* Device pointer of a derived table (for callers that fuse their own kernels). */
+VCM_API const int32_t *vcm_tables_device_ptr(const vcm_tables *t, int which);
+
+/* -------------------------------------------------- gather / contract (K1) --
+ * z[b,p,m,i] = sum_n [idx[p,n] != P_in] * A[p,n,m] * x[b, idx[p,n], i]
+ * Replaces graphVAESSW.py:111-123 (mask, zero-pad, index_select, einsum
+ * 'pnm,bpni->bpmi'). With M = 1 and A = normalised |p_neighbors| it is also
+ * the residual pool/unpool of graphVAESSW.py:152-159. */
+VCM_API int vcm_gather_contract_fwd(const vcm_tables *t, const float *x, const float *A, float *z,
+                                    int B, int I, int M, void *stream);
+
+/* Backward of the above w.r.t. A and the gathered rows (K5):
+ *   dA[p,n,m]   = sum_{b,i} dz[b,p,m,i] * x[b, idx[p,n], i]     (0 on padding)
+ *   dG[b,p,n,i] = sum_m A[p,n,m] * dz[b,p,m,i]                  (real edges only)
+ * dG is [B,P_out,N,I]; padding slots are left untouched and never read. dG may
+ * be NULL when the input gradient is not needed (first layer).
+ * workspace: fp32, at least vcm_coeff_grad_workspace() elements (may be NULL
+ * when that returns 0). Deterministic: fixed reduction order, no atomics. */
+VCM_API size_t vcm_coeff_grad_workspace(const vcm_tables *t, int B, int I, int M);
+VCM_API int vcm_coeff_grad(const vcm_tables *t, const float *dz, const float *x, const float *A, float *dA,
+                           float *dG, float *workspace, int B, int I, int M, void *stream);
+
+/* dX by the reverse (CSR-transposed) neighbour list (K6), no atomics:
+ *   dx[b,q,i] = sum_{slot in rev(q)} dG[b, slot, i]  (+ dx[b,q,i] if accumulate)
+ * Replaces the index_add_ scatter autograd runs for graphVAESSW.py:122. */
+VCM_API int vcm_scatter_rev(const vcm_tables *t, const float *dG, float *dx, int B, int I, int accumulate,
+                            void *stream);
+
+/* Residual edge weights, graphVAESSW.py:155-157:
+ *   pn[p,n] = |p_nb[p,n]| * mask / (sum_n |p_nb[p,n]| * mask + 1e-8)
+ * and its backward (dp_nb from dpn). */
+VCM_API int vcm_edge_weights_fwd(const vcm_tables *t, const float *p_nb, float *pn, void *stream);
+VCM_API int vcm_edge_weights_bwd(const vcm_tables *t, const float *p_nb, const float *dpn, float *dp_nb,
+                                 void *stream);
+
+/* ------------------------------------------------------ basis GEMMs (K2-K4) --
+ * K2 forward, replaces graphVAESSW.py:125-138 and the blend of :161:
+ *   t[r,o]   = sum_{m,i} z[r,m,i] * W[m,o,i] + bias
+ *   y        = act ? ELU(t) : t                (stored to y_act when non-NULL)
+ *   out      = y * scale_y + (res ? res * scale_res : 0)
+ * rows r = b*P_out + p; bias is [P_out,O] when bias_per_point, [O] otherwise,
+ * NULL for none. out may alias nothing else. */
+VCM_API int vcm_basis_fwd(const float *z, const float *W, const float *bias, int bias_per_point,
+                          const float *res, float *y_act, float *out, int B, int P_out, int M, int I, int O,
+                          int act, float scale_y, float scale_res, int precision, void *stream);
+
+/* Activation backward + bias gradient in one pass:
+ *   ds[r,o]     = dout[r,o] * scale_y * (act ? (y>0 ? 1 : y+1) : 1)
+ *   dbias[p,o]  = sum_b ds[b,p,o]          (dbias may be NULL)
+ *   dres[r,o]   = dout[r,o] * scale_res    (dres may be NULL)
+ * dbias is always the per-point [P_out,O] sum; for a shared bias reduce it
+ * with vcm_colsum. */
+VCM_API int vcm_act_bwd(const float *dout, const float *y_act, float *ds, float *dbias, float *dres, int B,
+                        int P_out, int O, int act, float scale_y, float scale_res, void *stream);
+VCM_API int vcm_colsum(const float *src, float *dst, int rows, int cols, void *stream);
+
+/* K3: dz[r,m,i] = sum_o ds[r,o] * W[m,o,i]  (+ dz if accumulate) */
+VCM_API int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t rows, int M, int I, int O,
+                             int accumulate, int precision, void *stream);
+
+/* K4: dW[m,o,i] = sum_r ds[r,o] * z[r,m,i]. workspace: fp32, at least
+ * vcm_basis_bwd_dw_workspace() elements. Deterministic split reduction. */
+VCM_API size_t vcm_basis_bwd_dw_workspace(int64_t rows, int M, int I, int O, int precision);
+VCM_API int vcm_basis_bwd_dw(const float *ds, const float *z, float *dW, float *workspace, int64_t rows,
+                             int M, int I, int O, int precision, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,83 @@
+"""ctypes binding of libvcmesh.so (include/vcmesh.h).
+
+The library is the product: if it cannot be loaded the import of any op fails
+loudly — there is no eager / PyTorch / CPU fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+import re
+
+from . import build as _build
+
+_lib = None
+
+PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
+TAB_IDX, TAB_LAST, TAB_PERM, TAB_REV_PTR, TAB_REV_SLOT = range(5)
+
+_p, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+
+
+class TablesInfo(C.Structure):
+    _fields_ = [("p_in", C.c_int32), ("p_out", C.c_int32), ("n_max", C.c_int32), ("max_last", C.c_int32),
+                ("nnz", C.c_int64), ("max_rev", C.c_int32), ("device", C.c_int32)]
+
+
+# name -> (restype, argtypes); must list every VCM_API symbol of include/vcmesh.h
+SIGNATURES = {
+    "vcm_last_error": (C.c_char_p, []),
+    "vcm_version": (_i, []),
+    "vcm_basis_uses_tensor_cores": (_i, [_i64, _i, _i, _i, _i]),
+    "vcm_tables_create": (_i, [_p, _i, _i, _i, C.POINTER(_p)]),
+    "vcm_tables_destroy": (None, [_p]),
+    "vcm_tables_get_info": (_i, [_p, C.POINTER(TablesInfo)]),
+    "vcm_tables_export": (_i, [_p, _i, _p, _sz]),
+    "vcm_tables_device_ptr": (_p, [_p, _i]),
+    "vcm_gather_contract_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "vcm_coeff_grad_workspace": (_sz, [_p, _i, _i, _i]),
+    "vcm_coeff_grad": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "vcm_scatter_rev": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "vcm_edge_weights_fwd": (_i, [_p, _p, _p, _p]),
+    "vcm_edge_weights_bwd": (_i, [_p, _p, _p, _p, _p]),
+    "vcm_basis_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p]),
+    "vcm_act_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p]),
+    "vcm_colsum": (_i, [_p, _p, _i, _i, _p]),
+    "vcm_basis_bwd_dz": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, _p]),
+    "vcm_basis_bwd_dw_workspace": (_sz, [_i64, _i, _i, _i, _i]),
+    "vcm_basis_bwd_dw": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
+}
+
+
+def declared_symbols():
+    """Every VCM_API function include/vcmesh.h declares (used by the CPU tests)."""
+    hdr = open(os.path.join(_build.ROOT, "include", "vcmesh.h")).read()
+    return sorted(set(re.findall(r"VCM_API[^;(]*?\b(vcm_\w+)\s*\(", hdr)))
+
+
+class VcmError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.LIB_CUDA
+        if not os.path.exists(path):
+            _build.build_cuda()          # raises if nvcc is unavailable: no fallback
+        L = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)        # AttributeError = ABI drift, fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise VcmError("libvcmesh: %s (code %d)" % (lib().vcm_last_error().decode(), code))
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

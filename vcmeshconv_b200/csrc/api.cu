@@ -1,0 +1,70 @@
+// C-ABI entry points of the basis GEMMs: argument checks + back-end choice.
+#include "gemm.h"
+
+using namespace vcm;
+
+static int check_gemm(int64_t R, int M, int I, int O, int precision) {
+    VCM_CHECK(R >= 0 && M > 0 && I > 0 && O > 0, "bad GEMM shape rows=%lld M=%d I=%d O=%d", (long long)R, M, I, O);
+    VCM_CHECK((int64_t)M * I < (1 << 24) && R < ((int64_t)1 << 31), "GEMM shape out of range");
+    VCM_CHECK(precision >= VCM_PREC_FP32 && precision <= VCM_PREC_TF32X3, "unknown precision %d", precision);
+    return VCM_OK;
+}
+
+extern "C" {
+
+int vcm_basis_uses_tensor_cores(int64_t rows, int M, int I, int O, int precision) {
+    return precision != VCM_PREC_FP32 && tc_supported(TC_FWD, rows, M, I, O, precision) ? 1 : 0;
+}
+
+int vcm_basis_fwd(const float *z, const float *W, const float *bias, int bias_per_point, const float *res,
+                  float *y_act, float *out, int B, int P_out, int M, int I, int O, int act, float scale_y,
+                  float scale_res, int precision, void *stream) {
+    VCM_CHECK(B > 0 && P_out >= 0, "bad batch / vertex count");
+    const int64_t R = (int64_t)B * P_out;
+    if (int e = check_gemm(R, M, I, O, precision)) return e;
+    VCM_DEVPTR(z); VCM_DEVPTR(W); VCM_DEVPTR(out);
+    VCM_DEVPTR_OPT(bias); VCM_DEVPTR_OPT(res); VCM_DEVPTR_OPT(y_act);
+    if (R == 0) return VCM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision != VCM_PREC_FP32 && tc_supported(TC_FWD, R, M, I, O, precision))
+        return tc_basis_fwd(z, W, bias, bias_per_point, res, y_act, out, R, P_out, M, I, O, act, scale_y, scale_res,
+                            precision, st);
+    return simt_basis_fwd(z, W, bias, bias_per_point, res, y_act, out, R, P_out, M, I, O, act, scale_y, scale_res, st);
+}
+
+int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t rows, int M, int I, int O, int accumulate,
+                     int precision, void *stream) {
+    if (int e = check_gemm(rows, M, I, O, precision)) return e;
+    VCM_DEVPTR(ds); VCM_DEVPTR(W); VCM_DEVPTR(dz);
+    if (rows == 0) return VCM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision != VCM_PREC_FP32 && tc_supported(TC_DZ, rows, M, I, O, precision))
+        return tc_basis_bwd_dz(ds, W, dz, rows, M, I, O, accumulate, precision, st);
+    return simt_basis_bwd_dz(ds, W, dz, rows, M, I, O, accumulate, st);
+}
+
+size_t vcm_basis_bwd_dw_workspace(int64_t rows, int M, int I, int O, int precision) {
+    if (rows <= 0 || M <= 0 || I <= 0 || O <= 0) return 0;
+    size_t a = simt_basis_bwd_dw_workspace(rows, M, I, O);
+    if (precision != VCM_PREC_FP32 && tc_supported(TC_DW, rows, M, I, O, precision)) {
+        const size_t b = tc_basis_bwd_dw_workspace(rows, M, I, O, precision);
+        a = a > b ? a : b;
+    }
+    return a;
+}
+
+int vcm_basis_bwd_dw(const float *ds, const float *z, float *dW, float *workspace, int64_t rows, int M, int I, int O,
+                     int precision, void *stream) {
+    if (int e = check_gemm(rows, M, I, O, precision)) return e;
+    VCM_DEVPTR(ds); VCM_DEVPTR(z); VCM_DEVPTR(dW); VCM_DEVPTR(workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) {
+        VCM_CUDA(cudaMemsetAsync(dW, 0, (size_t)M * I * O * sizeof(float), st));
+        return VCM_OK;
+    }
+    if (precision != VCM_PREC_FP32 && tc_supported(TC_DW, rows, M, I, O, precision))
+        return tc_basis_bwd_dw(ds, z, dW, workspace, rows, M, I, O, precision, st);
+    return simt_basis_bwd_dw(ds, z, dW, workspace, rows, M, I, O, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,549 @@
+// Gather-side kernels of the vc-conv hot path (K1, K5, K6 + residual edge weights).
+//
+//   K1  z[b,p,m,i]  = sum_n A[p,n,m] x[b,idx[p,n],i]            graphVAESSW.py:111-123
+//   K5  dA[p,n,m]   = sum_{b,i} dz[b,p,m,i] x[b,idx[p,n],i]      (autograd of :123 wrt A)
+//       dG[b,p,n,i] = sum_m A[p,n,m] dz[b,p,m,i]                 (autograd of :123 wrt G)
+//   K6  dx[b,q,i]   = sum_{slot in rev(q)} dG[b,slot,i]          (autograd of :122, index_add_)
+//
+// Work decomposition (all three): a "column" is one (b, i..i+VEC) strip of a
+// vertex row, VEC = 4 floats (128-bit loads/stores) whenever I % 4 == 0. A CTA
+// of 256 threads owns TP vertices x CB = 256/TP columns; vertices are taken in
+// the degree-bucketed order `perm`, so the TP rows of a CTA (and the warps of
+// neighbouring CTAs) have near-equal trip counts. The per-vertex coefficient
+// rows A[p,:,:] and neighbour ids are staged once per CTA in shared memory and
+// read back as warp-wide broadcasts; neighbour rows of x come straight from
+// L2 (x of a layer is a few MB and stays resident) as coalesced >=128 B
+// segments. The sentinel id P_in is tested in the loop: no mask tensor, no
+// zero-padded copy of x. All reductions have a fixed order: results are
+// bitwise reproducible and there are no atomics.
+#include "common.cuh"
+
+namespace vcm {
+
+constexpr int kThreads = 256;
+
+__host__ __device__ constexpr int round4(int m) { return (m + 3) / 4 * 4; }
+
+struct ColumnGeom {
+    int C;      // columns per vertex = B * I / VEC
+    int TP;     // vertices per CTA
+    int CB;     // columns per CTA pass = kThreads / TP
+    int IV;     // I / VEC
+};
+
+static ColumnGeom column_geom(int B, int I, int vec, int max_tp) {
+    ColumnGeom g;
+    g.IV = I / vec;
+    g.C = B * g.IV;
+    int tp = 1;
+    while (tp < max_tp && kThreads / (tp * 2) >= g.C) tp *= 2;   // shrink CB while it still covers C
+    g.TP = tp;
+    g.CB = kThreads / tp;
+    return g;
+}
+
+// ------------------------------------------------------------------ K1 ------
+template <int MT, int VEC>
+__global__ void __launch_bounds__(kThreads, (MT > 17 ? 1 : 2))
+gather_contract_fwd_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ last,
+                           const int32_t *__restrict__ perm, const float *__restrict__ x,
+                           const float *__restrict__ A, float *__restrict__ z, int p_in, int p_out, int n_max,
+                           int I, int M, ColumnGeom g) {
+    constexpr int MP = round4(MT);
+    extern __shared__ __align__(16) float smem[];
+    float *A_s = smem;                                               // [TP][n_max][MP]
+    int32_t *idx_s = reinterpret_cast<int32_t *>(smem + (size_t)g.TP * n_max * MP);  // [TP][n_max]
+    __shared__ int32_t vert_s[8], last_s[8];
+
+    const int tid = threadIdx.x;
+    if (tid < g.TP) {
+        const int slot = blockIdx.x * g.TP + tid;
+        const int p = slot < p_out ? perm[slot] : -1;
+        vert_s[tid] = p;
+        last_s[tid] = p >= 0 ? last[p] : 0;
+    }
+    __syncthreads();
+    for (int v = 0; v < g.TP; ++v) {
+        const int p = vert_s[v], l = last_s[v];
+        if (p < 0) continue;
+        const float *Ap = A + (size_t)p * n_max * M;
+        for (int e = tid; e < l * MP; e += kThreads) {
+            const int n = e / MP, m = e - n * MP;
+            A_s[((size_t)v * n_max + n) * MP + m] = m < M ? __ldg(Ap + n * M + m) : 0.f;
+        }
+        for (int n = tid; n < l; n += kThreads) idx_s[v * n_max + n] = __ldg(idx + (size_t)p * n_max + n);
+    }
+    __syncthreads();
+
+    const int v = tid / g.CB;
+    const int c = blockIdx.y * g.CB + (tid - v * g.CB);
+    const int p = vert_s[v];
+    if (p < 0 || c >= g.C) return;
+    const int b = c / g.IV, i0 = (c - b * g.IV) * VEC;
+    const float *xb = x + (size_t)b * p_in * I + i0;
+    const float *Av = A_s + (size_t)v * n_max * MP;
+    const int32_t *iv = idx_s + v * n_max;
+    const int l = last_s[v];
+
+    float acc[MT][VEC];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[m][j] = 0.f;
+
+#pragma unroll 2
+    for (int n = 0; n < l; ++n) {
+        const int q = iv[n];
+        if (q == p_in) continue;
+        Vec<VEC> gv;
+        gv.load(xb + (size_t)q * I);
+        const float4 *a4 = reinterpret_cast<const float4 *>(Av + n * MP);
+        float a[MP];
+#pragma unroll
+        for (int k = 0; k < MP / 4; ++k) {
+            const float4 t = a4[k];
+            a[4 * k] = t.x; a[4 * k + 1] = t.y; a[4 * k + 2] = t.z; a[4 * k + 3] = t.w;
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[m][j] = fmaf(a[m], gv.v[j], acc[m][j]);
+    }
+
+    float *zr = z + ((size_t)b * p_out + p) * M * I + i0;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        if (m < M) {
+            Vec<VEC> o;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) o.v[j] = acc[m][j];
+            o.store(zr + (size_t)m * I);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K5 ------
+// Butterfly transpose-reduce: every lane enters with vals[0..MT), lane l leaves
+// with the warp-wide sum of vals[l] in vals[0] (l < MT). 31 shuffles for
+// MT <= 32 instead of 5*MT.
+template <int MT>
+__device__ __forceinline__ float warp_transpose_reduce(float (&vals)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int j = 0; j < s; ++j) {
+            // values >= MT are structurally zero: the compiler drops their traffic
+            const float lo = vals[j], hi = vals[j + s];
+            const float send = upper ? lo : hi;
+            const float keep = upper ? hi : lo;
+            vals[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return vals[0];
+}
+
+template <int MT, int VEC>
+__global__ void __launch_bounds__(kThreads, 1)
+coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ last,
+                  const int32_t *__restrict__ perm, const float *__restrict__ dz, const float *__restrict__ x,
+                  const float *__restrict__ A, float *__restrict__ dA_out, float *__restrict__ dG, int p_in,
+                  int p_out, int n_max, int I, int M, ColumnGeom g, int passes_per_split, int n_split) {
+    constexpr int MP = round4(MT);
+    extern __shared__ __align__(16) float smem[];
+    float *A_s = smem;                                                 // [TP][n_max][MP]
+    float *part_s = A_s + (size_t)g.TP * n_max * MP;                   // [8 warps][n_max][MT]
+    int32_t *idx_s = reinterpret_cast<int32_t *>(part_s + (size_t)8 * n_max * MT);   // [TP][n_max]
+    __shared__ int32_t vert_s[8], last_s[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < g.TP) {
+        const int slot = blockIdx.x * g.TP + tid;
+        const int p = slot < p_out ? perm[slot] : -1;
+        vert_s[tid] = p;
+        last_s[tid] = p >= 0 ? last[p] : 0;
+    }
+    for (int e = tid; e < 8 * n_max * MT; e += kThreads) part_s[e] = 0.f;
+    __syncthreads();
+    for (int v = 0; v < g.TP; ++v) {
+        const int p = vert_s[v], l = last_s[v];
+        if (p < 0) continue;
+        const float *Ap = A + (size_t)p * n_max * M;
+        for (int e = tid; e < l * MP; e += kThreads) {
+            const int n = e / MP, m = e - n * MP;
+            A_s[((size_t)v * n_max + n) * MP + m] = m < M ? __ldg(Ap + n * M + m) : 0.f;
+        }
+        for (int n = tid; n < l; n += kThreads) idx_s[v * n_max + n] = __ldg(idx + (size_t)p * n_max + n);
+    }
+    __syncthreads();
+
+    // CB is a multiple of 32, so a warp never straddles two vertices.
+    const int v = tid / g.CB;
+    const int p = vert_s[v];
+    const int l = last_s[v];
+    const float *Av = A_s + (size_t)v * n_max * MP;
+    const int32_t *iv = idx_s + v * n_max;
+    float *pw = part_s + (size_t)warp * n_max * MT;
+
+    for (int pass = 0; pass < passes_per_split; ++pass) {
+        const int c = (blockIdx.y * passes_per_split + pass) * g.CB + (tid - v * g.CB);
+        const bool active = p >= 0 && c < g.C;
+        // warp-uniform early-out: nothing in this warp to do for this pass
+        if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+        const int b = active ? c / g.IV : 0, i0 = active ? (c - b * g.IV) * VEC : 0;
+        const float *xb = x + (size_t)b * p_in * I + i0;
+
+        float d[MT][VEC];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            Vec<VEC> t;
+            if (active && m < M) t.load(dz + (((size_t)b * p_out + p) * M + m) * I + i0);
+            else
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) t.v[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) d[m][j] = t.v[j];
+        }
+        float *dGr = dG + (((size_t)b * p_out + p) * n_max) * I + i0;
+
+        for (int n = 0; n < l; ++n) {
+            const int q = iv[n];
+            if (q == p_in) continue;                    // warp-uniform (same vertex)
+            Vec<VEC> gv;
+            if (active) gv.load(xb + (size_t)q * I);
+            else
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) gv.v[j] = 0.f;
+
+            // dG: A row (broadcast) x dz strip
+            const float4 *a4 = reinterpret_cast<const float4 *>(Av + n * MP);
+            float a[MP];
+#pragma unroll
+            for (int k = 0; k < MP / 4; ++k) {
+                const float4 t = a4[k];
+                a[4 * k] = t.x; a[4 * k + 1] = t.y; a[4 * k + 2] = t.z; a[4 * k + 3] = t.w;
+            }
+            Vec<VEC> og;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) og.v[j] = 0.f;
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) og.v[j] = fmaf(a[m], d[m][j], og.v[j]);
+            if (active && dG != nullptr) og.store(dGr + (size_t)n * I);
+
+            // dA: per-lane partial over the strip, then warp transpose-reduce
+            float vals[32];
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+                if (m < MT) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) s = fmaf(d[m][j], gv.v[j], s);
+                    vals[m] = s;
+                } else {
+                    vals[m] = 0.f;
+                }
+            }
+            const float tot = warp_transpose_reduce<MT>(vals, lane);
+            if (lane < MT) pw[n * MT + lane] += tot;     // warp-private slot: no race, fixed order
+        }
+    }
+    __syncthreads();
+
+    // cross-warp reduction in fixed warp order; padding slots get exactly 0
+    const int warps_per_v = g.CB / 32;
+    for (int e = tid; e < g.TP * n_max * M; e += kThreads) {
+        const int vv = e / (n_max * M);
+        const int r = e - vv * (n_max * M);
+        const int n = r / M, m = r - n * M;
+        const int pp = vert_s[vv];
+        if (pp < 0) continue;
+        float s = 0.f;
+        if (n < last_s[vv] && idx_s[vv * n_max + n] != p_in) {
+            for (int w = 0; w < warps_per_v; ++w) s += part_s[((size_t)(vv * warps_per_v + w) * n_max + n) * MT + m];
+        }
+        dA_out[((size_t)blockIdx.y * p_out + pp) * n_max * M + (size_t)n * M + m] = s;
+    }
+}
+
+__global__ void sum_splits_kernel(const float *__restrict__ part, float *__restrict__ out, size_t n, int n_split) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int k = 0; k < n_split; ++k) s += part[(size_t)k * n + i];
+    out[i] = s;
+}
+
+// ------------------------------------------------------------------ K6 ------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+scatter_rev_kernel(const int32_t *__restrict__ rev_ptr, const int32_t *__restrict__ rev_slot,
+                   const float *__restrict__ dG, float *__restrict__ dx, int p_in, int p_out, int n_max, int I,
+                   ColumnGeom g, int accumulate) {
+    const int tid = threadIdx.x;
+    const int v = tid / g.CB;
+    const int q = blockIdx.x * g.TP + v;
+    const int c = blockIdx.y * g.CB + (tid - v * g.CB);
+    if (q >= p_in || c >= g.C) return;
+    const int b = c / g.IV, i0 = (c - b * g.IV) * VEC;
+    const float *src = dG + (size_t)b * p_out * n_max * I + i0;
+    float *dst = dx + ((size_t)b * p_in + q) * I + i0;
+    const int e0 = __ldg(rev_ptr + q), e1 = __ldg(rev_ptr + q + 1);
+
+    float acc[VEC];
+    if (accumulate) {
+        Vec<VEC> t;
+        t.load(dst);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = t.v[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    }
+    int e = e0;
+    for (; e + 4 <= e1; e += 4) {                         // 4 independent gathers in flight
+        Vec<VEC> t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u].load(src + (size_t)__ldg(rev_slot + e + u) * I);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] += t[u].v[j];
+    }
+    for (; e < e1; ++e) {
+        Vec<VEC> t;
+        t.load(src + (size_t)__ldg(rev_slot + e) * I);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] += t.v[j];
+    }
+    Vec<VEC> o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o.v[j] = acc[j];
+    o.store(dst);
+}
+
+// ------------------------------------------------- residual edge weights ----
+__global__ void edge_weights_fwd_kernel(const int32_t *__restrict__ idx, const float *__restrict__ p_nb,
+                                        float *__restrict__ pn, int p_in, int p_out, int n_max) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p_out) return;
+    const int32_t *ir = idx + (size_t)p * n_max;
+    const float *pr = p_nb + (size_t)p * n_max;
+    float s = 0.f;
+    for (int n = 0; n < n_max; ++n) s += ir[n] != p_in ? fabsf(pr[n]) : 0.f;
+    s += 1e-8f;
+    for (int n = 0; n < n_max; ++n) pn[(size_t)p * n_max + n] = ir[n] != p_in ? fabsf(pr[n]) / s : 0.f;
+}
+
+__global__ void edge_weights_bwd_kernel(const int32_t *__restrict__ idx, const float *__restrict__ p_nb,
+                                        const float *__restrict__ dpn, float *__restrict__ dp, int p_in, int p_out,
+                                        int n_max) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p_out) return;
+    const int32_t *ir = idx + (size_t)p * n_max;
+    const float *pr = p_nb + (size_t)p * n_max;
+    const float *gr = dpn + (size_t)p * n_max;
+    float s = 0.f, dot = 0.f;
+    for (int n = 0; n < n_max; ++n)
+        if (ir[n] != p_in) {
+            s += fabsf(pr[n]);
+            dot += gr[n] * fabsf(pr[n]);
+        }
+    s += 1e-8f;
+    dot /= s;                                              // sum_k dpn[k] * pn[k]
+    for (int n = 0; n < n_max; ++n) {
+        float v = 0.f;
+        if (ir[n] != p_in) {
+            const float sg = pr[n] > 0.f ? 1.f : (pr[n] < 0.f ? -1.f : 0.f);
+            v = sg * (gr[n] - dot) / s;
+        }
+        dp[(size_t)p * n_max + n] = v;
+    }
+}
+
+// ------------------------------------------------------------ dispatch ------
+constexpr int kMaxSmem = 200 * 1024;
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) VCM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return VCM_OK;
+}
+
+template <int MT, int VEC>
+static int launch_fwd(const Tables *t, const float *x, const float *A, float *z, int B, int I, int M,
+                      cudaStream_t st) {
+    constexpr int MP = round4(MT);
+    ColumnGeom g = column_geom(B, I, VEC, 8);
+    auto bytes = [&](int tp) { return (size_t)tp * t->n_max * (MP + 1) * sizeof(float); };
+    while (g.TP > 1 && bytes(g.TP) > (size_t)kMaxSmem) { g.TP /= 2; g.CB *= 2; }
+    if (bytes(g.TP) > (size_t)kMaxSmem)
+        return fail(VCM_EUNSUPPORTED, "neighbour count %d too large for the staging buffer", t->n_max);
+    auto k = gather_contract_fwd_kernel<MT, VEC>;
+    if (int e = set_smem(k, bytes(g.TP))) return e;
+    dim3 grid((unsigned)ceil_div(t->p_out, g.TP), (unsigned)ceil_div(g.C, g.CB));
+    k<<<grid, kThreads, bytes(g.TP), st>>>(t->idx, t->last, t->perm, x, A, z, t->p_in, t->p_out, t->n_max, I, M, g);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+struct GradPlan {
+    ColumnGeom g;
+    int n_split, passes;
+    size_t smem;
+};
+
+template <int MT, int VEC>
+static int plan_grad(const Tables *t, int B, int I, GradPlan *pl) {
+    constexpr int MP = round4(MT);
+    ColumnGeom g = column_geom(B, I, VEC, 8);
+    auto bytes = [&](int tp) { return ((size_t)tp * t->n_max * (MP + 1) + (size_t)8 * t->n_max * MT) * sizeof(float); };
+    while (g.TP > 1 && bytes(g.TP) > (size_t)kMaxSmem) { g.TP /= 2; g.CB *= 2; }
+    if (bytes(g.TP) > (size_t)kMaxSmem)
+        return fail(VCM_EUNSUPPORTED, "neighbour count %d too large for the staging buffer", t->n_max);
+    const int64_t bx = ceil_div(t->p_out, g.TP), total_passes = ceil_div(g.C, g.CB);
+    int64_t split = ceil_div(2 * (int64_t)sm_count(), bx > 0 ? bx : 1);
+    if (split > total_passes) split = total_passes;
+    if (split < 1) split = 1;
+    pl->g = g;
+    pl->passes = (int)ceil_div(total_passes, split);
+    pl->n_split = (int)ceil_div(total_passes, pl->passes);
+    pl->smem = bytes(g.TP);
+    return VCM_OK;
+}
+
+template <int MT, int VEC>
+static int launch_grad(const Tables *t, const float *dz, const float *x, const float *A, float *dA, float *dG,
+                       float *ws, int B, int I, int M, cudaStream_t st) {
+    GradPlan pl;
+    if (int e = plan_grad<MT, VEC>(t, B, I, &pl)) return e;
+    auto k = coeff_grad_kernel<MT, VEC>;
+    if (int e = set_smem(k, pl.smem)) return e;
+    const size_t n_dA = (size_t)t->p_out * t->n_max * M;
+    if (pl.n_split > 1 && ws == nullptr) return fail(VCM_EINVAL, "workspace required (%d splits)", pl.n_split);
+    float *target = pl.n_split > 1 ? ws : dA;
+    dim3 grid((unsigned)ceil_div(t->p_out, pl.g.TP), (unsigned)pl.n_split);
+    k<<<grid, kThreads, pl.smem, st>>>(t->idx, t->last, t->perm, dz, x, A, target, dG, t->p_in, t->p_out, t->n_max,
+                                       I, M, pl.g, pl.passes, pl.n_split);
+    VCM_LAUNCH_CHECK();
+    if (pl.n_split > 1) {
+        sum_splits_kernel<<<(unsigned)ceil_div((int64_t)n_dA, 256), 256, 0, st>>>(ws, dA, n_dA, pl.n_split);
+        VCM_LAUNCH_CHECK();
+    }
+    return VCM_OK;
+}
+
+// smallest compiled accumulator height covering M
+#define VCM_DISPATCH_M(M, VEC, CALL)                                   \
+    do {                                                               \
+        if ((M) == 1) { constexpr int MT = 1; return CALL; }           \
+        if ((M) <= 8) { constexpr int MT = 8; return CALL; }           \
+        if ((M) <= 17) { constexpr int MT = 17; return CALL; }         \
+        if ((M) <= 32) { constexpr int MT = 32; return CALL; }         \
+        return fail(VCM_EUNSUPPORTED, "weight_num %d > 32 not built", (M)); \
+    } while (0)
+
+static int check_common(const Tables *t, int B, int I, int M) {
+    VCM_CHECK(t != nullptr, "tables handle is NULL");
+    VCM_CHECK(B > 0 && I > 0 && M > 0, "B, I, M must be positive (got %d, %d, %d)", B, I, M);
+    VCM_CHECK((int64_t)B * t->p_out * t->n_max * (int64_t)I < ((int64_t)1 << 40), "problem too large");
+    return VCM_OK;
+}
+
+}  // namespace vcm
+
+using namespace vcm;
+
+extern "C" {
+
+int vcm_gather_contract_fwd(const vcm_tables *h, const float *x, const float *A, float *z, int B, int I, int M,
+                            void *stream) {
+    const Tables *t = as_tables(h);
+    if (int e = check_common(t, B, I, M)) return e;
+    VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR(z);
+    if (t->p_out == 0) return VCM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v4 = I % 4 == 0 && aligned16(x) && aligned16(z);
+    if (v4) VCM_DISPATCH_M(M, 4, (launch_fwd<MT, 4>(t, x, A, z, B, I, M, st)));
+    VCM_DISPATCH_M(M, 1, (launch_fwd<MT, 1>(t, x, A, z, B, I, M, st)));
+}
+
+size_t vcm_coeff_grad_workspace(const vcm_tables *h, int B, int I, int M) {
+    const Tables *t = as_tables(h);
+    if (!t || B <= 0 || I <= 0 || M <= 0 || M > 32 || t->p_out == 0) return 0;
+    GradPlan pl;
+    int e;
+    const int mt = M == 1 ? 1 : M <= 8 ? 8 : M <= 17 ? 17 : 32;
+    // the plan depends on VEC only through the column count; be conservative: take the larger need
+    size_t need = 0;
+    for (int vec = 1; vec <= 4; vec += 3) {
+        if (vec == 4 && I % 4 != 0) continue;
+        switch (mt) {
+            case 1: e = vec == 4 ? plan_grad<1, 4>(t, B, I, &pl) : plan_grad<1, 1>(t, B, I, &pl); break;
+            case 8: e = vec == 4 ? plan_grad<8, 4>(t, B, I, &pl) : plan_grad<8, 1>(t, B, I, &pl); break;
+            case 17: e = vec == 4 ? plan_grad<17, 4>(t, B, I, &pl) : plan_grad<17, 1>(t, B, I, &pl); break;
+            default: e = vec == 4 ? plan_grad<32, 4>(t, B, I, &pl) : plan_grad<32, 1>(t, B, I, &pl); break;
+        }
+        if (e == VCM_OK && pl.n_split > 1) {
+            const size_t n = (size_t)pl.n_split * t->p_out * t->n_max * M;
+            need = n > need ? n : need;
+        }
+    }
+    return need;
+}
+
+int vcm_coeff_grad(const vcm_tables *h, const float *dz, const float *x, const float *A, float *dA, float *dG,
+                   float *ws, int B, int I, int M, void *stream) {
+    const Tables *t = as_tables(h);
+    if (int e = check_common(t, B, I, M)) return e;
+    VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
+    if (t->p_out == 0) return VCM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v4 = I % 4 == 0 && aligned16(x) && aligned16(dz) && (dG == nullptr || aligned16(dG));
+    if (v4) VCM_DISPATCH_M(M, 4, (launch_grad<MT, 4>(t, dz, x, A, dA, dG, ws, B, I, M, st)));
+    VCM_DISPATCH_M(M, 1, (launch_grad<MT, 1>(t, dz, x, A, dA, dG, ws, B, I, M, st)));
+}
+
+int vcm_scatter_rev(const vcm_tables *h, const float *dG, float *dx, int B, int I, int accumulate, void *stream) {
+    const Tables *t = as_tables(h);
+    if (int e = check_common(t, B, I, 1)) return e;
+    VCM_DEVPTR(dG); VCM_DEVPTR(dx);
+    if (t->p_in == 0) return VCM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v4 = I % 4 == 0 && aligned16(dG) && aligned16(dx);
+    ColumnGeom g = column_geom(B, I, v4 ? 4 : 1, 8);
+    dim3 grid((unsigned)ceil_div(t->p_in, g.TP), (unsigned)ceil_div(g.C, g.CB));
+    if (v4)
+        scatter_rev_kernel<4><<<grid, kThreads, 0, st>>>(t->rev_ptr, t->rev_slot, dG, dx, t->p_in, t->p_out, t->n_max,
+                                                         I, g, accumulate);
+    else
+        scatter_rev_kernel<1><<<grid, kThreads, 0, st>>>(t->rev_ptr, t->rev_slot, dG, dx, t->p_in, t->p_out, t->n_max,
+                                                         I, g, accumulate);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+int vcm_edge_weights_fwd(const vcm_tables *h, const float *p_nb, float *pn, void *stream) {
+    const Tables *t = as_tables(h);
+    VCM_CHECK(t != nullptr, "tables handle is NULL");
+    VCM_DEVPTR(p_nb); VCM_DEVPTR(pn);
+    if (t->p_out == 0 || t->n_max == 0) return VCM_OK;
+    edge_weights_fwd_kernel<<<(unsigned)ceil_div(t->p_out, 128), 128, 0, (cudaStream_t)stream>>>(
+        t->idx, p_nb, pn, t->p_in, t->p_out, t->n_max);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+int vcm_edge_weights_bwd(const vcm_tables *h, const float *p_nb, const float *dpn, float *dp, void *stream) {
+    const Tables *t = as_tables(h);
+    VCM_CHECK(t != nullptr, "tables handle is NULL");
+    VCM_DEVPTR(p_nb); VCM_DEVPTR(dpn); VCM_DEVPTR(dp);
+    if (t->p_out == 0 || t->n_max == 0) return VCM_OK;
+    edge_weights_bwd_kernel<<<(unsigned)ceil_div(t->p_out, 128), 128, 0, (cudaStream_t)stream>>>(
+        t->idx, p_nb, dpn, dp, t->p_in, t->p_out, t->n_max);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+// fp32 CUDA-core versions of the basis GEMMs (K2, K3, K4) + the elementwise
+// activation backward. These are the exact-fp32 arithmetic mode
+// (VCM_PREC_FP32) and the fallback for shapes the tcgen05 kernels in
+// gemm_tc.cu do not take (K = 17*3 = 51 on the first layer, O = 3 on the
+// last, tiny row counts).
+//
+//   K2  t[r,o]  = sum_{m,i} z[r,m,i] W[m,o,i]            graphVAESSW.py:125-133
+//       out     = ELU(t + bias) * sy + res * sr           graphVAESSW.py:135-138,161
+//   K3  dz[r,m,i] = sum_o ds[r,o] W[m,o,i]                (autograd of :126)
+//   K4  dW[m,o,i] = sum_r ds[r,o] z[r,m,i]                (autograd of :126)
+//
+// W is consumed in the reference's native parameter layout [M][O][I]
+// (`weights.view(M, O, I)`, graphVAESSW.py:125): element (k = m*I + i, o) lives
+// at (m*O + o)*I + i, so no transposed copy of the bases is ever made.
+#include "common.cuh"
+
+namespace vcm {
+
+__device__ __forceinline__ float elu1(float t) { return t > 0.f ? t : expm1f(t); }
+
+// address of basis element (k, o), k = m*I + i
+__device__ __forceinline__ size_t basis_addr(int k, int o, int I, int O) {
+    const int m = k / I, i = k - m * I;
+    return ((size_t)m * O + o) * I + i;
+}
+
+constexpr int BM = 128, BN = 64, BK = 16, GT = 256;
+
+struct FwdEpilogue {
+    const float *bias;   // may be null
+    const float *res;    // may be null
+    float *y_act;        // may be null
+    float *out;
+    int P_out, O, per_point, act;
+    float sy, sr;
+    __device__ __forceinline__ void operator()(int64_t r, int o, float acc) const {
+        float t = acc;
+        if (bias) t += __ldg(bias + (per_point ? (size_t)(r % P_out) * O : 0) + o);
+        const float y = act ? elu1(t) : t;
+        const size_t at = (size_t)r * O + o;
+        if (y_act) y_act[at] = y;
+        float v = y * sy;
+        if (res) v = fmaf(__ldg(res + at), sr, v);
+        out[at] = v;
+    }
+};
+
+struct DzEpilogue {
+    float *dz;
+    int K, accumulate;
+    __device__ __forceinline__ void operator()(int64_t r, int k, float acc) const {
+        const size_t at = (size_t)r * K + k;
+        dz[at] = accumulate ? dz[at] + acc : acc;
+    }
+};
+
+// C[r, n] = sum_k A[r, k] * Bop(k, n);  A row-major [R, Kd].
+//   B_KN = true : reduction index is the basis k = (m,i), n = o     (K2)
+//   B_KN = false: reduction index is o, n = the basis k = (m,i)     (K3)
+template <bool B_KN, typename Epi>
+__global__ void __launch_bounds__(GT) gemm_rows_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                       int64_t R, int Kd, int Nd, int I, int O, Epi epi) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int ty = tid / 16, tx = tid % 16;          // 16 x 16 threads, 8 x 4 outputs each
+    const int64_t r0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const bool a_vec = (Kd % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < Kd; k0 += BK) {
+        // ---- A tile: BM rows x BK reduction, stored transposed ----
+        if (a_vec) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int f = tid + GT * u;
+                const int row = f >> 2, k4 = (f & 3) * 4;
+                const int64_t r = r0 + row;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < R && k0 + k4 < Kd) v = ldg4(A + (size_t)r * Kd + k0 + k4);
+                As[k4 + 0][row] = v.x; As[k4 + 1][row] = v.y; As[k4 + 2][row] = v.z; As[k4 + 3][row] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + GT * u;
+                const int row = e >> 4, kk = e & 15;
+                const int64_t r = r0 + row;
+                As[kk][row] = (r < R && k0 + kk < Kd) ? __ldg(A + (size_t)r * Kd + k0 + kk) : 0.f;
+            }
+        }
+        // ---- B tile: BK reduction x BN ----
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + GT * u;
+            int kk, nn;
+            if (B_KN) { kk = e & 15; nn = e >> 4; }     // contiguous along the basis index i
+            else      { nn = e & 63; kk = e >> 6; }
+            const int kg = k0 + kk, ng = n0 + nn;
+            float v = 0.f;
+            if (kg < Kd && ng < Nd) v = B_KN ? __ldg(W + basis_addr(kg, ng, I, O)) : __ldg(W + basis_addr(ng, kg, I, O));
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = r0 + ty * 8 + i;
+        if (r >= R) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < Nd) epi(r, n, acc[i][j]);
+        }
+    }
+}
+
+// K2 for a handful of output channels (last decoder layer, O = 3): one warp per
+// row, lanes stride the reduction; the bases sit in shared memory as [o][k].
+template <int OT>
+__global__ void __launch_bounds__(256) gemm_rows_small_o_kernel(const float *__restrict__ z,
+                                                                const float *__restrict__ W, int64_t R, int K, int I,
+                                                                int O, FwdEpilogue epi) {
+    extern __shared__ float Ws[];   // [O][K]
+    for (int e = threadIdx.x; e < O * K; e += blockDim.x) {
+        const int o = e / K, k = e - o * K;
+        Ws[e] = __ldg(W + basis_addr(k, o, I, O));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * nw + warp; r < R; r += (int64_t)gridDim.x * nw) {
+        const float *zr = z + (size_t)r * K;
+        float acc[OT];
+#pragma unroll
+        for (int o = 0; o < OT; ++o) acc[o] = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float v = __ldg(zr + k);
+#pragma unroll
+            for (int o = 0; o < OT; ++o)
+                if (o < O) acc[o] = fmaf(v, Ws[o * K + k], acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < OT; ++o)
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+#pragma unroll
+        for (int o = 0; o < OT; ++o)
+            if (o < O && lane == o) epi(r, o, acc[o]);
+    }
+}
+
+// K4: part[s][k][o] = sum_{r in split s} z[r,k] ds[r,o]; 64 x 64 tile, rows in steps of 16.
+constexpr int DK = 64, DO = 64, DR = 16;
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const float *__restrict__ z, const float *__restrict__ ds,
+                                                      float *__restrict__ part, int64_t R, int K, int O,
+                                                      int64_t rows_per_split) {
+    __shared__ __align__(16) float Zs[DR][DK + 4];
+    __shared__ __align__(16) float Ds[DR][DO + 4];
+    const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+    const int k0 = blockIdx.x * DK, o0 = blockIdx.y * DO;
+    const int64_t rs = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t re = rs + rows_per_split < R ? rs + rows_per_split : R;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int64_t r0 = rs; r0 < re; r0 += DR) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + 256 * u;
+            const int rr = e >> 6, cc = e & 63;
+            const int64_t r = r0 + rr;
+            Zs[rr][cc] = (r < re && k0 + cc < K) ? __ldg(z + (size_t)r * K + k0 + cc) : 0.f;
+            Ds[rr][cc] = (r < re && o0 + cc < O) ? __ldg(ds + (size_t)r * O + o0 + cc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < DR; ++rr) {
+            const float4 a = *reinterpret_cast<const float4 *>(&Zs[rr][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Ds[rr][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *dst = part + (size_t)blockIdx.z * K * O;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty * 4 + i;
+        if (k >= K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + tx * 4 + j;
+            if (o < O) dst[(size_t)k * O + o] = acc[i][j];
+        }
+    }
+}
+
+// dW[m][o][i] = sum_s part[s][k = m*I+i][o], fixed order
+__global__ void reduce_dw_kernel(const float *__restrict__ part, float *__restrict__ dW, int K, int O, int I,
+                                 int n_split) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into dW's native layout
+    if (e >= (size_t)K * O) return;
+    const int i = (int)(e % I);
+    const size_t mo = e / I;
+    const int o = (int)(mo % O), m = (int)(mo / O);
+    const size_t src = ((size_t)m * I + i) * O + o;
+    float s = 0.f;
+    for (int k = 0; k < n_split; ++k) s += part[(size_t)k * K * O + src];
+    dW[e] = s;
+}
+
+// ds / dbias / dres in one pass; one thread per (p, o), loop over the batch.
+__global__ void act_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ y, float *__restrict__ ds,
+                               float *__restrict__ dbias, float *__restrict__ dres, int B, int P_out, int O, int act,
+                               float sy, float sr) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // p * O + o
+    const size_t PO = (size_t)P_out * O;
+    if (e >= PO) return;
+    float sum = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const size_t at = (size_t)b * PO + e;
+        const float g = __ldg(dout + at);
+        float d = g * sy;
+        if (act) {
+            const float yy = __ldg(y + at);
+            d = yy > 0.f ? d : d * (yy + 1.f);
+        }
+        ds[at] = d;
+        sum += d;
+        if (dres) dres[at] = g * sr;
+    }
+    if (dbias) dbias[e] = sum;
+}
+
+// dst[c] = sum_r src[r, c]: one block per 32 columns, fixed-order tree
+__global__ void colsum_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int w = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < cols)
+        for (int r = w; r < rows; r += 8) s += __ldg(src + (size_t)r * cols + c);
+    red[w][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (w == 0 && c < cols) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+        dst[c] = t;
+    }
+}
+
+// ---- host-side planners shared with gemm_tc.cu ------------------------------
+struct DwPlan { int n_split; int64_t rows_per_split; };
+static DwPlan plan_dw(int64_t R, int K, int O) {
+    const int64_t tiles = ceil_div(K, DK) * ceil_div(O, DO);
+    int64_t split = ceil_div(4 * (int64_t)sm_count(), tiles);
+    const int64_t max_split = ceil_div(R, 8 * DR);
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+    DwPlan p;
+    p.rows_per_split = ceil_div(ceil_div(R, split), DR) * DR;
+    p.n_split = (int)ceil_div(R, p.rows_per_split);
+    if (p.n_split < 1) p.n_split = 1;
+    return p;
+}
+
+int simt_basis_fwd(const float *z, const float *W, const float *bias, int per_point, const float *res, float *y_act,
+                   float *out, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr,
+                   cudaStream_t st) {
+    const int K = M * I;
+    FwdEpilogue epi{bias, res, y_act, out, P_out, O, per_point, act, sy, sr};
+    if (O <= 8 && (size_t)O * K * sizeof(float) <= 96 * 1024) {
+        const size_t smem = (size_t)O * K * sizeof(float);
+        auto k = O <= 4 ? gemm_rows_small_o_kernel<4> : gemm_rows_small_o_kernel<8>;
+        if (smem > 48 * 1024) VCM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t blocks = ceil_div(R, 8);
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        k<<<(unsigned)blocks, 256, smem, st>>>(z, W, R, K, I, O, epi);
+    } else {
+        dim3 grid((unsigned)ceil_div(R, BM), (unsigned)ceil_div(O, BN));
+        gemm_rows_kernel<true, FwdEpilogue><<<grid, GT, 0, st>>>(z, W, R, K, O, I, O, epi);
+    }
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+int simt_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t R, int M, int I, int O, int accumulate,
+                      cudaStream_t st) {
+    const int K = M * I;
+    DzEpilogue epi{dz, K, accumulate};
+    dim3 grid((unsigned)ceil_div(R, BM), (unsigned)ceil_div(K, BN));
+    gemm_rows_kernel<false, DzEpilogue><<<grid, GT, 0, st>>>(ds, W, R, O, K, I, O, epi);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+size_t simt_basis_bwd_dw_workspace(int64_t R, int M, int I, int O) {
+    const DwPlan p = plan_dw(R, M * I, O);
+    return (size_t)p.n_split * M * I * O;
+}
+
+int simt_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64_t R, int M, int I, int O,
+                      cudaStream_t st) {
+    const int K = M * I;
+    const DwPlan p = plan_dw(R, K, O);
+    dim3 grid((unsigned)ceil_div(K, DK), (unsigned)ceil_div(O, DO), (unsigned)p.n_split);
+    gemm_tn_kernel<<<grid, 256, 0, st>>>(z, ds, ws, R, K, O, p.rows_per_split);
+    VCM_LAUNCH_CHECK();
+    reduce_dw_kernel<<<(unsigned)ceil_div((int64_t)K * O, 256), 256, 0, st>>>(ws, dW, K, O, I, p.n_split);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+}  // namespace vcm
+
+using namespace vcm;
+
+extern "C" {
+
+int vcm_act_bwd(const float *dout, const float *y_act, float *ds, float *dbias, float *dres, int B, int P_out, int O,
+                int act, float scale_y, float scale_res, void *stream) {
+    VCM_CHECK(B > 0 && P_out >= 0 && O > 0, "bad shape");
+    VCM_DEVPTR(dout); VCM_DEVPTR(ds); VCM_DEVPTR_OPT(dbias); VCM_DEVPTR_OPT(dres);
+    if (act) VCM_DEVPTR(y_act);
+    if (P_out == 0) return VCM_OK;
+    act_bwd_kernel<<<(unsigned)ceil_div((int64_t)P_out * O, 256), 256, 0, (cudaStream_t)stream>>>(
+        dout, y_act, ds, dbias, dres, B, P_out, O, act, scale_y, scale_res);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+int vcm_colsum(const float *src, float *dst, int rows, int cols, void *stream) {
+    VCM_CHECK(rows >= 0 && cols > 0, "bad shape");
+    VCM_DEVPTR(src); VCM_DEVPTR(dst);
+    colsum_kernel<<<(unsigned)ceil_div(cols, 32), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, cols);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+"""torch.autograd.Functions over the C ABI of libvcmesh.so.
+
+PyTorch is plumbing here: it owns the device buffers, the stream and the
+autograd tape. Every arithmetic step of the layer is one of our kernels:
+
+  gather_contract   K1 fwd / K5 + K6 bwd       graphVAESSW.py:111-123
+  basis_gemm        K2 fwd / act_bwd+K3+K4 bwd graphVAESSW.py:125-138, :161
+  edge_weights      residual |p| normalisation graphVAESSW.py:155-157
+  vcconv            the whole layer            graphVAESSW.py:97-163
+
+Tensors must be CUDA fp32; CPU tensors raise (no fallback).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_precision = _lib.PREC_FP32
+
+
+def set_precision(name):
+    """'fp32' (CUDA-core FMA, the reference's arithmetic), 'tf32' or 'tf32x3'
+    (tcgen05 tensor cores; see include/vcmesh.h). Returns the previous mode."""
+    global _precision
+    prev = {v: k for k, v in _lib.PRECISIONS.items()}[_precision]
+    _precision = _lib.PRECISIONS[name]
+    return prev
+
+
+def get_precision():
+    return {v: k for k, v in _lib.PRECISIONS.items()}[_precision]
+
+
+def _req(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: vcmeshconv_b200 has no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class _GatherContract(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, A, tables):
+        x, A = _req(x, "x"), _req(A, "coefficients")
+        B, p_in, I = x.shape
+        if p_in != tables.p_in:
+            raise RuntimeError("x has %d vertices, table expects %d" % (p_in, tables.p_in))
+        if A.dim() != 3 or A.shape[0] != tables.p_out or A.shape[1] != tables.n_max:
+            raise RuntimeError("coefficients must be [%d, %d, M], got %s" % (tables.p_out, tables.n_max, tuple(A.shape)))
+        M = A.shape[2]
+        z = torch.empty(B, tables.p_out, M * I, device=x.device, dtype=torch.float32)
+        if B:
+            _lib.check(_lib.lib().vcm_gather_contract_fwd(tables.handle, _ptr(x), _ptr(A), _ptr(z), B, I, M,
+                                                          _lib.stream_ptr()))
+        ctx.save_for_backward(x, A)
+        ctx.tables = tables
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, A = ctx.saved_tensors
+        t = ctx.tables
+        B, p_in, I = x.shape
+        M = A.shape[2]
+        need_dx, need_dA = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_dx or need_dA) or B == 0:
+            return (torch.zeros_like(x) if need_dx else None), (torch.zeros_like(A) if need_dA else None), None
+        dz = _req(dz, "dz")
+        L = _lib.lib()
+        dA = torch.empty_like(A)
+        dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
+        n_ws = L.vcm_coeff_grad_workspace(t.handle, B, I, M)
+        ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
+        st = _lib.stream_ptr()
+        _lib.check(L.vcm_coeff_grad(t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M, st))
+        dx = None
+        if need_dx:
+            dx = torch.empty_like(x)
+            _lib.check(L.vcm_scatter_rev(t.handle, _ptr(dG), _ptr(dx), B, I, 0, st))
+        return dx, (dA if need_dA else None), None
+
+
+class _BasisGemm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, W, bias, res, M, I, O, act, scale_y, scale_res, precision):
+        z, W = _req(z, "z"), _req(W, "weights")
+        B, p_out, K = z.shape
+        if K != M * I or W.numel() != M * O * I:
+            raise RuntimeError("basis GEMM shape mismatch: z %s, weights %s, M=%d I=%d O=%d" %
+                               (tuple(z.shape), tuple(W.shape), M, I, O))
+        per_point = 0
+        if bias is not None:
+            bias = _req(bias, "bias")
+            if bias.dim() == 2:
+                if tuple(bias.shape) != (p_out, O):
+                    raise RuntimeError("per-point bias must be [%d, %d]" % (p_out, O))
+                per_point = 1
+            elif tuple(bias.shape) != (O,):
+                raise RuntimeError("shared bias must be [%d]" % O)
+        if res is not None:
+            res = _req(res, "residual")
+            if tuple(res.shape) != (B, p_out, O):
+                raise RuntimeError("residual must be [%d, %d, %d], got %s" % (B, p_out, O, tuple(res.shape)))
+        out = torch.empty(B, p_out, O, device=z.device, dtype=torch.float32)
+        # the activated value is what ELU' needs; it is `out` itself unless a blend follows
+        y_act = None
+        if act and (res is not None or scale_y != 1.0):
+            y_act = torch.empty_like(out)
+        if B and p_out:
+            _lib.check(_lib.lib().vcm_basis_fwd(_ptr(z), _ptr(W), _ptr(bias), per_point, _ptr(res), _ptr(y_act),
+                                                _ptr(out), B, p_out, M, I, O, int(act), scale_y, scale_res,
+                                                precision, _lib.stream_ptr()))
+        y_saved = (y_act if y_act is not None else out) if act else None
+        ctx.save_for_backward(z, W, y_saved)
+        ctx.cfg = (M, I, O, int(act), scale_y, scale_res, precision, per_point, bias is not None, res is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, W, y = ctx.saved_tensors
+        M, I, O, act, sy, sr, precision, per_point, has_bias, has_res = ctx.cfg
+        B, p_out, K = z.shape
+        need_dz, need_dW, need_db, need_dres = (ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                                has_bias and ctx.needs_input_grad[2],
+                                                has_res and ctx.needs_input_grad[3])
+        dout = _req(dout, "dout")
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        dev = z.device
+        if B == 0 or p_out == 0:
+            return (torch.zeros_like(z), torch.zeros_like(W),
+                    (torch.zeros(p_out, O, device=dev) if per_point else torch.zeros(O, device=dev)) if need_db else None,
+                    torch.zeros_like(dout) if need_dres else None) + (None,) * 7
+        ds = torch.empty_like(dout)
+        db_pp = torch.empty(p_out, O, device=dev, dtype=torch.float32) if need_db else None
+        dres = torch.empty_like(dout) if need_dres else None
+        _lib.check(L.vcm_act_bwd(_ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st))
+        dbias = None
+        if need_db:
+            if per_point:
+                dbias = db_pp
+            else:
+                dbias = torch.empty(O, device=dev, dtype=torch.float32)
+                _lib.check(L.vcm_colsum(_ptr(db_pp), _ptr(dbias), p_out, O, st))
+        R = B * p_out
+        dz = dW = None
+        if need_dz:
+            dz = torch.empty_like(z)
+            _lib.check(L.vcm_basis_bwd_dz(_ptr(ds), _ptr(W), _ptr(dz), R, M, I, O, 0, precision, st))
+        if need_dW:
+            dW = torch.empty_like(W)
+            n_ws = L.vcm_basis_bwd_dw_workspace(R, M, I, O, precision)
+            ws = torch.empty(max(n_ws, 1), device=dev, dtype=torch.float32)
+            _lib.check(L.vcm_basis_bwd_dw(_ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision, st))
+        return (dz, dW, dbias, dres) + (None,) * 7
+
+
+class _EdgeWeights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p_nb, tables):
+        p_nb = _req(p_nb, "p_neighbors")
+        if tuple(p_nb.shape) != (tables.p_out, tables.n_max):
+            raise RuntimeError("p_neighbors must be [%d, %d]" % (tables.p_out, tables.n_max))
+        pn = torch.empty_like(p_nb)
+        _lib.check(_lib.lib().vcm_edge_weights_fwd(tables.handle, _ptr(p_nb), _ptr(pn), _lib.stream_ptr()))
+        ctx.save_for_backward(p_nb)
+        ctx.tables = tables
+        return pn
+
+    @staticmethod
+    def backward(ctx, dpn):
+        (p_nb,) = ctx.saved_tensors
+        dpn = _req(dpn, "dpn")
+        dp = torch.empty_like(p_nb)
+        _lib.check(_lib.lib().vcm_edge_weights_bwd(ctx.tables.handle, _ptr(p_nb), _ptr(dpn), _ptr(dp),
+                                                   _lib.stream_ptr()))
+        return dp, None
+
+
+def gather_contract(x, coeffs, tables):
+    """z[b,p,m*I+i] = sum_n coeffs[p,n,m] * x[b, idx[p,n], i] over real neighbours."""
+    return _GatherContract.apply(x, coeffs, tables)
+
+
+def basis_gemm(z, weights, bias, res, M, I, O, act, scale_y=1.0, scale_res=0.0, precision=None):
+    """out = (act ? ELU : id)(z @ stacked(weights) + bias) * scale_y + res * scale_res."""
+    return _BasisGemm.apply(z, weights, bias, res, M, I, O, bool(act), float(scale_y), float(scale_res),
+                            _precision if precision is None else precision)
+
+
+def edge_weights(p_neighbors, tables):
+    return _EdgeWeights.apply(p_neighbors, tables)
+
+
+def blend_scales(residual_rate):
+    """sqrt(1-r), sqrt(r) as the reference applies them to fp32 tensors
+    (np.sqrt of a python float, graphVAESSW.py:161)."""
+    return float(np.float32(np.sqrt(1 - residual_rate))), float(np.float32(np.sqrt(residual_rate)))
+
+
+def vcconv(x, coeffs, weights, bias, tables, *, is_final_layer=False, residual_rate=0.0, p_neighbors=None,
+           weight_res=None, precision=None):
+    """One vc-conv / vd-pool / vd-unpool layer (LASMConvssw.forward,
+    graphVAESSW.py:97-163) on the CUDA kernels."""
+    B, p_in, I = x.shape
+    M = weights.shape[0]
+    O = weights.shape[1] // I
+    z = gather_contract(x, coeffs, tables)
+    act = not is_final_layer
+    if residual_rate == 0:
+        return basis_gemm(z, weights, bias, None, M, I, O, act, 1.0, 0.0, precision)
+    sy, sr = blend_scales(residual_rate)
+    xr = x
+    if I != O:                                   # :144-145, 1x1 projection = basis GEMM with one basis, no bias
+        xr = basis_gemm(x, weight_res, None, None, 1, I, O, False, 1.0, 0.0, precision)
+    if p_in == tables.p_out:                     # :148-149 identity skip
+        res = xr
+    else:                                        # :151-159 weighted pool / unpool of the projected rows
+        pn = edge_weights(p_neighbors, tables)
+        res = gather_contract(xr, pn.unsqueeze(-1), tables)
+    return basis_gemm(z, weights, bias, res, M, I, O, act, sy, sr, precision)
