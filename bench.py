@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the vc-conv hot path: training meshes/sec of the D-FAUST-shaped
+mesh autoencoder (BASELINE.json metric), fwd + bwd + gradient all-reduce + Adam.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload at every N (weak scaling): BASELINE config C2 — the 6+6-layer
+autoencoder of graphVAE_train.py:151,172 on a synthetic 6890-vertex
+SMPL-topology template (convex-hull sphere: 6890 v / 13776 f), per-GPU batch
+16, residual_rate 0.9, per-point bias, M = 17, fp32 data, synthetic meshes.
+
+One JSON line on stdout (rank 0). `value` = meshes/s with the batch already
+resident in HBM; `e2e` = the same step through the public trainer API with the
+batch copied from pinned host memory and the loss read back every step.
+`--impl reference` times the CPU restatement of the reference (oracle/) on the
+host cores; it is also the `cpu_baseline` of the default run (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_VERT = 6890
+BATCH = 16
+N_LEVELS = 7
+RESIDUAL = 0.9
+METRIC = "training meshes/sec (fwd+bwd) D-FAUST AE"
+WORKLOAD = "C2: D-FAUST-shaped AE, 6890-vertex sphere template, 6+6 layers [3,32,64,128,256,512,64], M=17, " \
+           "residual 0.9, batch 16 per GPU"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("VCM_PRECISION", "auto"))
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--vertices", type=int, default=N_VERT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------
+# synthetic data of the reference's shape (graphVAE_train.py:96-123: vertices in
+# metres, unit face normals)
+# ---------------------------------------------------------------------------------
+def synthetic_batch(pts, faces, batch, seed):
+    import numpy as np
+    from vcmeshconv_b200 import synthetic
+    rng = np.random.default_rng(seed)
+    pc = (pts[None] * 0.9 + rng.standard_normal((batch,) + pts.shape).astype(np.float32) * 0.02).astype(np.float32)
+    nor = synthetic.face_normals(pc, faces).astype(np.float32)
+    return pc, nor
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1]); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ---------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference, on the host cores
+# ---------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, tabs, pts, faces):
+    import torch
+    from oracle import vcconv_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    enc = [tabs["pool%d" % l] for l in range(1, 7)]
+    dec = [tabs["unpool%d" % l] for l in range(6, 0, -1)]
+    ae = orc.AutoEncoder(enc, dec, len(pts), tabs["pool0"], faces, residual_rate=RESIDUAL, seed=0).requires_grad_(True)
+    opt = torch.optim.Adam(ae.parameters(), lr=1e-4, betas=(0.9, 0.999))    # graphVAE_train.py:260
+    pc, nor = synthetic_batch(pts, faces, args.batch, 0)
+    pc, nor = torch.from_numpy(pc), torch.from_numpy(nor)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        eps = torch.randn(args.batch, *ae.latent_shape)
+        loss = ae.losses(pc, nor, eps)[0]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return args.batch / mean, mean * 1e3, torch.get_num_threads()
+
+
+def build_tables(n_vert):
+    from vcmeshconv_b200 import graph_sampling, synthetic
+    pts, faces = synthetic.sphere(n_vert, seed=0)
+    tabs, nums = graph_sampling.build_tables(faces, n_vert, synthetic.alternating_levels(N_LEVELS))
+    return pts, faces, tabs, nums
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pts, faces, tabs, _ = build_tables(args.vertices)
+    value, ms, cores = cpu_reference_run(args, args.steps, args.warmup, tabs, pts, faces)
+    sample = "%d warm-up + %d timed full steps (fwd+bwd+Adam) of batch %d on the host cores" % (args.warmup, args.steps, args.batch)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "meshes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": args.batch, "vertices": args.vertices,
+                   "note": "CPU restatement of the reference (oracle/vcconv_oracle.py, same ATen op sequence as "
+                           "graphVAESSW.py:97-163); the Python reference itself cannot travel to the GPU box"},
+        "cpu_baseline": {"value": value, "unit": "meshes/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vcmeshconv_b200 import _lib, functional as F_
+    from vcmeshconv_b200 import graphVAE_train as T
+
+    rank, local, world = T.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    precision = args.precision
+    if precision == "auto":
+        precision = os.environ.get("VCM_DEFAULT_PRECISION", "fp32")
+    F_.set_precision(precision)
+
+    pts, faces, tabs, nums = build_tables(args.vertices)
+    enc = [tabs["pool%d" % l] for l in range(1, 7)]
+    dec = [tabs["unpool%d" % l] for l in range(6, 0, -1)]
+    param = T.make_param(enc, dec, tabs["pool0"], len(pts), RESIDUAL)
+    torch.manual_seed(0)
+    model = T.Net_autoenc(param, faces).to(dev)
+    trainer = T.DataParallelTrainer(model, lr=1e-4)
+    n_params = sum(p.numel() for p in model.trainable_parameters())
+
+    # a few distinct synthetic batches, rotated; the step's own working set (GBs of intermediates)
+    # is far larger than the 126 MB L2, so nothing stays cached from one step to the next
+    n_rot = 4
+    host = [synthetic_batch(pts, faces, args.batch, 1000 * rank + i) for i in range(n_rot)]
+    pin = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(n).pin_memory()) for p, n in host]
+    resident = [(p.to(dev), n.to(dev)) for p, n in pin]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.lib().vcm_launch_count()
+        t0 = time.time()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _lib.lib().vcm_launch_count() - l0, t0, t1
+
+    def step_resident(i):
+        pc, nor = resident[i % n_rot]
+        trainer.step(pc, nor)
+
+    dev_pc = torch.empty_like(resident[0][0])
+    dev_nor = torch.empty_like(resident[0][1])
+    loss_host = torch.zeros(1).pin_memory()
+    h2d = dev_pc.numel() * 4 + dev_nor.numel() * 4
+
+    def step_e2e(i):
+        hp, hn = pin[i % n_rot]
+        dev_pc.copy_(hp, non_blocking=True)
+        dev_nor.copy_(hn, non_blocking=True)
+        loss, _ = trainer.step(dev_pc, dev_nor)
+        loss_host.copy_(loss.reshape(1), non_blocking=False)       # device -> host read of the step's result
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, t0, t1 = timed(step_resident, args.steps)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+
+    gbatch = args.batch * world
+    value = gbatch * args.steps / (ms / 1e3)
+    e2e = gbatch * args.steps / (ms_e2e / 1e3)
+
+    roof, breakdown = None, None
+    if rank == 0 and not args.no_profile:
+        roof, breakdown = roofline(trainer, resident, n_rot, min(args.steps, 5))
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cms, cores = cpu_reference_run(args, args.cpu_steps, 1, tabs, pts, faces)
+        cpu = {"value": v, "unit": "meshes/s", "cores": cores, "kind": "port", "ms_per_step": cms,
+               "sample": "1 warm-up + %d timed full steps (fwd+bwd+Adam, batch %d) of oracle/vcconv_oracle.py on "
+                         "the host cores" % (args.cpu_steps, args.batch)}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "meshes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": gbatch, "vertices": args.vertices,
+                       "parallelism": "dp%d" % world, "gemm_precision": precision, "trainable_params": n_params,
+                       "point_nums": nums, "l2": "inputs rotate over %d batches; each step streams GBs of "
+                       "intermediates (>> 126 MB L2), nothing survives in L2 between steps" % n_rot},
+            "e2e": {"value": e2e, "unit": "meshes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "kernel_breakdown": breakdown}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline(trainer, resident, n_rot, steps):
+    """Per-entry-point CUDA-event timing of `steps` further training steps
+    (events on the launching stream). The dominant entry point's algorithmic
+    bytes (SURVEY §8d formulas, counted per call in functional.py) over its
+    summed duration is `achieved`."""
+    import torch
+    from vcmeshconv_b200 import _lib
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    with _lib.Profiler() as prof:
+        for i in range(steps):
+            pc, nor = resident[i % n_rot]
+            trainer.step(pc, nor)
+    summ = prof.summary()
+    total = sum(v["ms"] for v in summ.values())
+    breakdown = {k: {"ms_per_step": v["ms"] / steps, "share": v["ms"] / total, "calls_per_step": v["calls"] / steps,
+                     "GBps": v["bytes"] / v["ms"] / 1e6 if v["ms"] else None,
+                     "TFLOPs": v["flops"] / v["ms"] / 1e9 if v["ms"] else None} for k, v in summ.items()}
+    top = max(summ, key=lambda k: summ[k]["ms"])
+    v = summ[top]
+    achieved = v["bytes"] / v["ms"] / 1e6                      # GB/s
+    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+            "launches": v["calls"], "avg_launch_ms": v["ms"] / v["calls"],
+            "algorithmic_bytes_per_launch": v["bytes"] / v["calls"],
+            "how": "CUDA events around every call of this entry point on the launching stream, over %d steps "
+                   "run right after the timed region" % steps}
+    return roof, breakdown
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

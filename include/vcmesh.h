@@ -57,6 +57,8 @@ enum { VCM_PREC_FP32 = 0, VCM_PREC_TF32 = 1, VCM_PREC_TF32X3 = 2 };
 
 VCM_API const char *vcm_last_error(void);
 VCM_API int vcm_version(void);
+/* Diagnostics: number of CUDA kernels this library has launched in the process. */
+VCM_API unsigned long long vcm_launch_count(void);
 /* 1 when a tcgen05 kernel exists for this (rows, K, O) and precision. */
 VCM_API int vcm_basis_uses_tensor_cores(int64_t rows, int M, int I, int O, int precision);
 
@@ -158,6 +160,14 @@ VCM_API int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t
 VCM_API size_t vcm_basis_bwd_dw_workspace(int64_t rows, int M, int I, int O, int precision);
 VCM_API int vcm_basis_bwd_dw(const float *ds, const float *z, float *dW, float *workspace, int64_t rows,
                              int M, int I, int O, int precision, void *stream);
+
+/* ------------------------------------------------------------- optimizer --
+ * Fused Adam over one flat fp32 buffer; replaces torch.optim.Adam(lr,
+ * betas=(0.9, 0.999)) of graphVAE_train.py:252-262 / :316 (no weight decay, no
+ * amsgrad). `step` counts from 1. g is multiplied by grad_scale first (1 for
+ * the reference's SUM-over-replicas semantics). */
+VCM_API int vcm_adam_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1,
+                          float beta2, float eps, int step, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ class TablesInfo(C.Structure):
 SIGNATURES = {
     "vcm_last_error": (C.c_char_p, []),
     "vcm_version": (_i, []),
+    "vcm_launch_count": (C.c_ulonglong, []),
     "vcm_basis_uses_tensor_cores": (_i, [_i64, _i, _i, _i, _i]),
     "vcm_tables_create": (_i, [_p, _i, _i, _i, C.POINTER(_p)]),
     "vcm_tables_destroy": (None, [_p]),
@@ -45,6 +46,7 @@ SIGNATURES = {
     "vcm_basis_bwd_dz": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, _p]),
     "vcm_basis_bwd_dw_workspace": (_sz, [_i64, _i, _i, _i, _i]),
     "vcm_basis_bwd_dw": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
+    "vcm_adam_step": (_i, [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _i, _f, _p]),
 }
 
 
@@ -76,6 +78,59 @@ def lib():
 def check(code):
     if code != 0:
         raise VcmError("libvcmesh: %s (code %d)" % (lib().vcm_last_error().decode(), code))
+
+
+class Profiler:
+    """Per-call CUDA-event timing of the C-ABI compute calls (bench.py roofline).
+    Events are recorded on torch's current stream, which is the stream every
+    call is enqueued on. Use as a context manager; results after a synchronize."""
+
+    def __init__(self):
+        self.records = []          # (name, tag, bytes, flops, start_event, end_event)
+
+    def __enter__(self):
+        global _profiler
+        _profiler = self
+        return self
+
+    def __exit__(self, *exc):
+        global _profiler
+        _profiler = None
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, tag, nbytes, flops, e0, e1 in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0, "by_tag": {}})
+            ms = e0.elapsed_time(e1)
+            d["calls"] += 1
+            d["ms"] += ms
+            d["bytes"] += nbytes
+            d["flops"] += flops
+            t = d["by_tag"].setdefault(tag, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            t["calls"] += 1
+            t["ms"] += ms
+            t["bytes"] += nbytes
+            t["flops"] += flops
+        return out
+
+
+_profiler = None
+
+
+def call(name, *args, nbytes=0, flops=0, tag=""):
+    """Invoke one compute entry point; raises VcmError on a non-zero status."""
+    fn = getattr(lib(), name)
+    if _profiler is None:
+        check(fn(*args))
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args))
+    e1.record()
+    _profiler.records.append((name, tag, nbytes, flops, e0, e1))
 
 
 def stream_ptr():

@@ -27,8 +27,13 @@ int fail(int code, const char *fmt, ...);
         if (!(cond)) return ::vcm::fail(VCM_EINVAL, __VA_ARGS__); \
     } while (0)
 
+// diagnostics only: how many kernels this library has launched (bench.py's gpu_launches)
+void count_launch();
+unsigned long long launches();
+
 #define VCM_LAUNCH_CHECK()                                                                 \
     do {                                                                                   \
+        ::vcm::count_launch();                                                             \
         cudaError_t _e = cudaPeekAtLastError();                                            \
         if (_e != cudaSuccess)                                                             \
             return ::vcm::fail((int)_e, "kernel launch failed: %s (%s:%d)",                \

@@ -364,3 +364,43 @@ int vcm_colsum(const float *src, float *dst, int rows, int cols, void *stream) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Fused Adam over one flat parameter/gradient buffer: the
+// reference runs torch.optim.Adam(lr, betas=(0.9, 0.999)) over ~60 tensors
+// (graphVAE_train.py:252-262); here all parameters and gradients live in one
+// contiguous fp32 buffer (the same one NCCL reduces in place), so the whole
+// optimizer step is one launch. Arithmetic follows torch.optim.Adam (no weight
+// decay, no amsgrad): p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+namespace vcm {
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                            float *__restrict__ v, size_t n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float grad_scale) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * grad_scale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+}  // namespace vcm
+
+extern "C" int vcm_adam_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1,
+                             float beta2, float eps, int step, float grad_scale, void *stream) {
+    VCM_CHECK(step >= 1, "Adam step counter starts at 1");
+    VCM_DEVPTR(p); VCM_DEVPTR(g); VCM_DEVPTR(m); VCM_DEVPTR(v);
+    if (n == 0) return VCM_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    int64_t blocks = vcm::ceil_div((int64_t)n, 256 * 4);
+    const int64_t cap = (int64_t)vcm::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    vcm::adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1,
+                                                                         bc2_sqrt, grad_scale);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}

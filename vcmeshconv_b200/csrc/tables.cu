@@ -6,6 +6,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
 #include <numeric>
 #include <vector>
 
@@ -37,6 +38,10 @@ bool is_device_ptr(const void *p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -57,6 +62,7 @@ extern "C" {
 
 const char *vcm_last_error(void) { return vcm::last_error_slot().c_str(); }
 int vcm_version(void) { return 100; }
+unsigned long long vcm_launch_count(void) { return vcm::launches(); }
 
 int vcm_tables_create(const int32_t *table, int p_out, int cols, int p_in, vcm_tables **out) {
     VCM_CHECK(out != nullptr, "out is NULL");

@@ -57,8 +57,10 @@ class _GatherContract(torch.autograd.Function):
         M = A.shape[2]
         z = torch.empty(B, tables.p_out, M * I, device=x.device, dtype=torch.float32)
         if B:
-            _lib.check(_lib.lib().vcm_gather_contract_fwd(tables.handle, _ptr(x), _ptr(A), _ptr(z), B, I, M,
-                                                          _lib.stream_ptr()))
+            nnz = tables.nnz
+            _lib.call("vcm_gather_contract_fwd", tables.handle, _ptr(x), _ptr(A), _ptr(z), B, I, M, _lib.stream_ptr(),
+                      nbytes=4 * (x.numel() + nnz * M + nnz + z.numel()), flops=2 * B * nnz * M * I,
+                      tag="P%d>%d I%d M%d" % (p_in, tables.p_out, I, M))
         ctx.save_for_backward(x, A)
         ctx.tables = tables
         return z
@@ -79,11 +81,16 @@ class _GatherContract(torch.autograd.Function):
         n_ws = L.vcm_coeff_grad_workspace(t.handle, B, I, M)
         ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
         st = _lib.stream_ptr()
-        _lib.check(L.vcm_coeff_grad(t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M, st))
+        nnz, tag = t.nnz, "P%d>%d I%d M%d" % (p_in, t.p_out, I, M)
+        gb = 4 * B * nnz * I
+        _lib.call("vcm_coeff_grad", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M, st,
+                  nbytes=4 * (dz.numel() + x.numel() + 2 * nnz * M + nnz) + (gb if need_dx else 0),
+                  flops=(4 if need_dx else 2) * B * nnz * M * I, tag=tag)
         dx = None
         if need_dx:
             dx = torch.empty_like(x)
-            _lib.check(L.vcm_scatter_rev(t.handle, _ptr(dG), _ptr(dx), B, I, 0, st))
+            _lib.call("vcm_scatter_rev", t.handle, _ptr(dG), _ptr(dx), B, I, 0, st,
+                      nbytes=gb + 4 * nnz + 4 * (p_in + 1) + 4 * x.numel(), flops=B * nnz * I, tag=tag)
         return dx, (dA if need_dA else None), None
 
 
@@ -114,9 +121,11 @@ class _BasisGemm(torch.autograd.Function):
         if act and (res is not None or scale_y != 1.0):
             y_act = torch.empty_like(out)
         if B and p_out:
-            _lib.check(_lib.lib().vcm_basis_fwd(_ptr(z), _ptr(W), _ptr(bias), per_point, _ptr(res), _ptr(y_act),
-                                                _ptr(out), B, p_out, M, I, O, int(act), scale_y, scale_res,
-                                                precision, _lib.stream_ptr()))
+            nb = 4 * (z.numel() + W.numel() + (bias.numel() if bias is not None else 0) + out.numel() +
+                      (res.numel() if res is not None else 0) + (y_act.numel() if y_act is not None else 0))
+            _lib.call("vcm_basis_fwd", _ptr(z), _ptr(W), _ptr(bias), per_point, _ptr(res), _ptr(y_act), _ptr(out), B,
+                      p_out, M, I, O, int(act), scale_y, scale_res, precision, _lib.stream_ptr(),
+                      nbytes=nb, flops=2 * B * p_out * M * I * O, tag="R%d K%d O%d" % (B * p_out, M * I, O))
         y_saved = (y_act if y_act is not None else out) if act else None
         ctx.save_for_backward(z, W, y_saved)
         ctx.cfg = (M, I, O, int(act), scale_y, scale_res, precision, per_point, bias is not None, res is not None)
@@ -141,24 +150,31 @@ class _BasisGemm(torch.autograd.Function):
         ds = torch.empty_like(dout)
         db_pp = torch.empty(p_out, O, device=dev, dtype=torch.float32) if need_db else None
         dres = torch.empty_like(dout) if need_dres else None
-        _lib.check(L.vcm_act_bwd(_ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st))
+        ny = dout.numel()
+        tag = "R%d K%d O%d" % (B * p_out, K, O)
+        _lib.call("vcm_act_bwd", _ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st,
+                  nbytes=4 * (ny * (2 + (1 if act else 0) + (1 if need_dres else 0)) + (p_out * O if need_db else 0)),
+                  flops=2 * ny, tag=tag)
         dbias = None
         if need_db:
             if per_point:
                 dbias = db_pp
             else:
                 dbias = torch.empty(O, device=dev, dtype=torch.float32)
-                _lib.check(L.vcm_colsum(_ptr(db_pp), _ptr(dbias), p_out, O, st))
+                _lib.call("vcm_colsum", _ptr(db_pp), _ptr(dbias), p_out, O, st, nbytes=4 * (p_out * O + O),
+                          flops=p_out * O, tag=tag)
         R = B * p_out
         dz = dW = None
         if need_dz:
             dz = torch.empty_like(z)
-            _lib.check(L.vcm_basis_bwd_dz(_ptr(ds), _ptr(W), _ptr(dz), R, M, I, O, 0, precision, st))
+            _lib.call("vcm_basis_bwd_dz", _ptr(ds), _ptr(W), _ptr(dz), R, M, I, O, 0, precision, st,
+                      nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
         if need_dW:
             dW = torch.empty_like(W)
             n_ws = L.vcm_basis_bwd_dw_workspace(R, M, I, O, precision)
             ws = torch.empty(max(n_ws, 1), device=dev, dtype=torch.float32)
-            _lib.check(L.vcm_basis_bwd_dw(_ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision, st))
+            _lib.call("vcm_basis_bwd_dw", _ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision, st,
+                      nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
         return (dz, dW, dbias, dres) + (None,) * 7
 
 
@@ -169,7 +185,8 @@ class _EdgeWeights(torch.autograd.Function):
         if tuple(p_nb.shape) != (tables.p_out, tables.n_max):
             raise RuntimeError("p_neighbors must be [%d, %d]" % (tables.p_out, tables.n_max))
         pn = torch.empty_like(p_nb)
-        _lib.check(_lib.lib().vcm_edge_weights_fwd(tables.handle, _ptr(p_nb), _ptr(pn), _lib.stream_ptr()))
+        _lib.call("vcm_edge_weights_fwd", tables.handle, _ptr(p_nb), _ptr(pn), _lib.stream_ptr(),
+                  nbytes=12 * p_nb.numel(), flops=3 * p_nb.numel())
         ctx.save_for_backward(p_nb)
         ctx.tables = tables
         return pn
@@ -179,8 +196,8 @@ class _EdgeWeights(torch.autograd.Function):
         (p_nb,) = ctx.saved_tensors
         dpn = _req(dpn, "dpn")
         dp = torch.empty_like(p_nb)
-        _lib.check(_lib.lib().vcm_edge_weights_bwd(ctx.tables.handle, _ptr(p_nb), _ptr(dpn), _ptr(dp),
-                                                   _lib.stream_ptr()))
+        _lib.call("vcm_edge_weights_bwd", ctx.tables.handle, _ptr(p_nb), _ptr(dpn), _ptr(dp), _lib.stream_ptr(),
+                  nbytes=16 * p_nb.numel(), flops=6 * p_nb.numel())
         return dp, None
 
 

@@ -1,0 +1,274 @@
+"""Training step of the mesh autoencoder, batch data-parallel over B200s.
+
+Mirrors the reference's GraphAutoEncoder/graphVAE_train.py for the part that
+is on the hot path (e):
+
+  Net_autoenc           graphVAE_train.py:132-249   same constructor, same
+                        sub-module names (checkpoint keys), same forward
+                        signature and 5-tuple of [1]-shaped losses
+  DataParallelTrainer   replaces nn.DataParallel (:277) + Adam (:252-262, :316):
+                        one process per GPU, parameters resident on every GPU,
+                        gradients produced directly inside ONE flat fp32 buffer
+                        that NCCL all-reduces in place (SUM — the reference sums
+                        per-replica mean losses, :249/:315), bucketed in reverse
+                        layer order and launched from autograd hooks so the
+                        reduction hides under the rest of backward; then one
+                        fused Adam launch over the flat buffers on every rank.
+
+Data IO (PLY), tensorboard and the INI reader are out of scope;
+`Parameters` below only carries the fields the model needs.
+"""
+import os
+import types
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib
+from . import graphVAESSW as vae_model
+
+ENC_CHANNELS = [3, 32, 64, 128, 256, 512, 64]      # graphVAE_train.py:151 (hard-coded there)
+DEC_CHANNELS = [64, 512, 256, 128, 64, 32, 3]      # graphVAE_train.py:172
+WEIGHT_NUM = 17                                    # graphVAE_train.py:136
+
+
+def make_param(enc_tables, dec_tables, table0, point_num, residual_rate=0.9, w_pose=1.0, w_laplace=100.0, lr=1e-4,
+               batch=16, conv_max=0, write_tmp_folder=""):
+    """The fields of the reference's `Parameters` object (graphAE_param_iso.py:21-134)
+    that the model reads; tables may be arrays or .npy paths."""
+    t0 = np.load(table0) if isinstance(table0, str) else np.asarray(table0)
+    return types.SimpleNamespace(
+        point_num=point_num, residual_rate=residual_rate, conv_max=conv_max, w_pose=w_pose, w_laplace=w_laplace,
+        lr=lr, batch=batch, write_tmp_folder=write_tmp_folder,
+        connection_layer_fn_lst_enc=list(enc_tables), connection_layer_fn_lst_dec=list(dec_tables),
+        neighbor_id_lstlst=t0[:, 1:].reshape(t0.shape[0], -1, 2)[:, :, 0], neighbor_num_lst=t0[:, 0])
+
+
+class Net_autoenc(nn.Module):
+    def __init__(self, param, facedata, enc_channels=None, dec_channels=None, weight_num=WEIGHT_NUM):
+        super().__init__()
+        self.weight_num = weight_num
+        self.motdim = 94
+        enc_channels = ENC_CHANNELS if enc_channels is None else enc_channels
+        dec_channels = DEC_CHANNELS if dec_channels is None else dec_channels
+        self.mcstructureenc = vae_model.MCStructure(param, param.point_num, weight_num, bDec=False)
+        self.mcvcoeffsenc = vae_model.MCVcoeffs(self.mcstructureenc, weight_num)
+        self.net_geoenc = vae_model.MCEnc(self.mcstructureenc, enc_channels, weight_num)
+        self.nrpt_latent = self.net_geoenc.out_nrpts
+        self.mcstructuredec = vae_model.MCStructure(param, self.nrpt_latent, weight_num, bDec=True)
+        self.mcvcoeffsdec = vae_model.MCVcoeffs(self.mcstructuredec, weight_num)
+        self.net_geodec = vae_model.MCDec(self.mcstructuredec, dec_channels, weight_num)
+        self.net_loss = vae_model.MCLoss(param)
+        self.register_buffer("t_facedata", torch.as_tensor(np.asarray(facedata)).long())
+        self.w_pose = param.w_pose
+        self.w_laplace = param.w_laplace
+        self.klweight = 1e-5
+        self.w_nor = 10.0
+        self.write_tmp_folder = getattr(param, "write_tmp_folder", "")
+
+    def losses(self, in_pc_batch, t_nor, t_eps=None):
+        """graphVAE_train.py:199-225. `t_eps` lets a caller fix the N(0,1) draw."""
+        t_mu, t_logstd = self.net_geoenc(in_pc_batch, self.mcvcoeffsenc)
+        t_std = t_logstd.exp()
+        if t_eps is None:
+            t_eps = torch.ones_like(t_std).normal_()
+        t_z = t_mu + t_std * t_eps
+        klloss = torch.mean(-0.5 - t_logstd + 0.5 * t_mu ** 2 + 0.5 * torch.exp(2 * t_logstd))
+        out_pc_batch = self.net_geodec(t_z, self.mcvcoeffsdec)[:, :, 0:3]
+        dif_pos = out_pc_batch - in_pc_batch
+        f = self.t_facedata
+        tri = dif_pos[:, f[:, 0]] + dif_pos[:, f[:, 1]] + dif_pos[:, f[:, 2]]
+        loss_normal = (tri / 3.0 * t_nor).sum(2).pow(2).mean()
+        loss_pose_l1 = self.net_loss.compute_geometric_loss_l1(in_pc_batch[:, :, 0:3], out_pc_batch)
+        loss_laplace = self.net_loss.compute_laplace_loss_l2(in_pc_batch[:, :, 0:3], out_pc_batch)
+        loss = (loss_pose_l1 * self.w_pose + loss_laplace * self.w_laplace + klloss * self.klweight +
+                loss_normal * self.w_nor)
+        return loss, loss_pose_l1, loss_laplace, klloss, loss_normal, out_pc_batch
+
+    def forward(self, in_pc_batch, iteration=0, frame=None, t_idx=None, t_nor=None, bDebug=False):
+        loss, l1, lap, kl, nor, _ = self.losses(in_pc_batch, t_nor)
+        return loss[None], l1[None], lap[None], kl[None], nor[None]
+
+    def trainable_parameters(self):
+        """Same parameter set and order as the reference's getoptim (graphVAE_train.py:252-262)."""
+        import itertools
+        return [p for p in itertools.chain(self.net_geodec.parameters(), self.net_geoenc.parameters(),
+                                           self.mcvcoeffsdec.parameters(), self.mcvcoeffsenc.parameters())
+                if p.requires_grad]
+
+
+class FlatBuffers:
+    """All trainable parameters (and their gradients) as views into two flat
+    fp32 buffers. Layout follows backward order (decoder last layer first) so a
+    bucket is a contiguous slice that becomes ready as a whole."""
+
+    def __init__(self, params, bucket_bytes=32 << 20):
+        params = list(params)
+        dev = params[0].device
+        # autograd reaches parameters roughly in reverse creation order of use; bucket order only
+        # affects overlap, never results
+        self.params = params
+        sizes = [p.numel() for p in params]
+        pad = lambda n: (n + 63) // 64 * 64               # 256-byte aligned views (vectorised kernels)
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += pad(n)
+        self.total = total
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.offsets = offs
+        for p, o in zip(params, offs):
+            n = p.numel()
+            self.flat_p[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + n].view(p.shape)
+            p.grad = self.flat_g[o:o + n].view(p.shape)
+        # buckets: consecutive parameters up to bucket_bytes
+        self.buckets, cur, cur_bytes, start = [], [], 0, 0
+        for i, n in enumerate(sizes):
+            cur.append(i)
+            cur_bytes += pad(n) * 4
+            if cur_bytes >= bucket_bytes or i == len(sizes) - 1:
+                end = offs[i] + pad(n)
+                self.buckets.append((start, end, list(cur)))
+                start, cur, cur_bytes = end, [], 0
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+
+class DataParallelTrainer:
+    """One rank of the batch-data-parallel training job.
+
+    step(pc, nor) = forward + backward + gradient all-reduce (SUM) + Adam.
+    world_size 1 needs no process group. Works with any torch.distributed
+    backend (NCCL on the GPUs; gloo in the CPU tests of the bucket logic)."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, bucket_bytes=32 << 20, process_group=None,
+                 overlap=True):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.flat = FlatBuffers(model.trainable_parameters(), bucket_bytes)
+        self.exp_avg = torch.zeros_like(self.flat.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat.flat_p)
+        self.step_count = 0
+        self.overlap = overlap and self.world > 1
+        self._pending = []
+        self._handles = []
+        if self.overlap:
+            self._install_hooks()
+        if self.world > 1:
+            self.broadcast_parameters()
+
+    # -- communication ------------------------------------------------------------
+    def broadcast_parameters(self):
+        """Rank 0's initial parameters everywhere (the reference replicates from GPU 0 every
+        forward; here they are resident and only synchronised once)."""
+        dist.broadcast(self.flat.flat_p, 0, group=self.group)
+
+    def _install_hooks(self):
+        owner = {}
+        for b, (_, _, idxs) in enumerate(self.flat.buckets):
+            for i in idxs:
+                owner[i] = b
+        self._remaining = [len(idxs) for _, _, idxs in self.flat.buckets]
+        self._count = list(self._remaining)
+        for i, p in enumerate(self.flat.params):
+            def hook(param, i=i):
+                b = owner[i]
+                self._count[b] -= 1
+                if self._count[b] == 0:
+                    self._launch_bucket(b)
+            p.register_post_accumulate_grad_hook(hook)
+
+    def _launch_bucket(self, b):
+        s, e, _ = self.flat.buckets[b]
+        self._handles.append(dist.all_reduce(self.flat.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.group,
+                                             async_op=True))
+
+    def _finish_reduction(self):
+        if self.world == 1:
+            return
+        if self.overlap:
+            for b, c in enumerate(self._count):          # parameters that received no gradient this step
+                if c != 0:
+                    self._launch_bucket(b)
+            self._count = list(self._remaining)
+            for h in self._handles:
+                h.wait()
+            self._handles = []
+        else:
+            dist.all_reduce(self.flat.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+
+    # -- one training step ---------------------------------------------------------
+    def forward_backward(self, pc, nor, eps=None):
+        self.flat.zero_grad()
+        loss, l1, lap, kl, lnor, _ = self.model.losses(pc, nor, eps)
+        loss.backward()
+        return loss.detach(), (l1.detach(), lap.detach(), kl.detach(), lnor.detach())
+
+    def optimizer_step(self):
+        self.step_count += 1
+        f = self.flat
+        if f.flat_p.is_cuda:
+            _lib.check(_lib.lib().vcm_adam_step(f.flat_p.data_ptr(), f.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                                self.exp_avg_sq.data_ptr(), f.total, self.lr, self.betas[0],
+                                                self.betas[1], self.eps, self.step_count, 1.0, _lib.stream_ptr()))
+        else:
+            raise RuntimeError("the optimizer step runs on CUDA only (no CPU fallback)")
+
+    def step(self, pc, nor, eps=None):
+        loss, parts = self.forward_backward(pc, nor, eps)
+        self._finish_reduction()
+        self.optimizer_step()
+        return loss, parts
+
+    # -- checkpoint layout of the reference (graphVAE_train.py:339-347) ----------
+    def state_dict(self):
+        m = self.model
+        return {"encgeo_state_dict": m.net_geoenc.state_dict(), "decgeo_state_dict": m.net_geodec.state_dict(),
+                "mcvcoeffsdec_dict": m.mcvcoeffsdec.state_dict(), "mcvcoeffsenc_dict": m.mcvcoeffsenc.state_dict(),
+                "optimizer_state_dict": {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}}
+
+    def load_model_state(self, ckpt):
+        m = self.model
+        with torch.no_grad():
+            for mod, key in ((m.net_geoenc, "encgeo_state_dict"), (m.net_geodec, "decgeo_state_dict"),
+                             (m.mcvcoeffsdec, "mcvcoeffsdec_dict"), (m.mcvcoeffsenc, "mcvcoeffsenc_dict")):
+                own = mod.state_dict()
+                for k, v in ckpt[key].items():
+                    own[k].copy_(v)              # in place: parameters stay views of the flat buffer
+
+
+def init_distributed():
+    """torchrun environment -> (rank, local_rank, world). NCCL over NVLink/NVSwitch."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local) if torch.cuda.is_available() else None)
+    return rank, local, world
+
+
+def build_synthetic_autoencoder(n_vert, n_levels=7, seed=0, residual_rate=0.9, template="sphere"):
+    """Synthetic template + tables + model as BASELINE config C2/C3 describes:
+    encoder tables pool1..pool6, decoder unpool6..unpool1 of the alternating
+    stride-1/2 hierarchy, 6+6 layers with the trainer's hard-coded channels."""
+    from . import graph_sampling, synthetic
+    pts, faces = getattr(synthetic, template)(n_vert, seed=seed) if template != "torus" else synthetic.torus()
+    tabs, nums = graph_sampling.build_tables(faces, len(pts), synthetic.alternating_levels(n_levels))
+    enc = [tabs["pool%d" % l] for l in range(1, 7)]
+    dec = [tabs["unpool%d" % l] for l in range(6, 0, -1)]
+    param = make_param(enc, dec, tabs["pool0"], len(pts), residual_rate)
+    torch.manual_seed(seed)
+    model = Net_autoenc(param, faces)
+    return model, pts, faces, tabs, nums
