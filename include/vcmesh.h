@@ -151,9 +151,12 @@ VCM_API int vcm_act_bwd(const float *dout, const float *y_act, float *ds, float 
                         int P_out, int O, int act, float scale_y, float scale_res, void *stream);
 VCM_API int vcm_colsum(const float *src, float *dst, int rows, int cols, void *stream);
 
-/* K3: dz[r,m,i] = sum_o ds[r,o] * W[m,o,i]  (+ dz if accumulate) */
-VCM_API int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t rows, int M, int I, int O,
-                             int accumulate, int precision, void *stream);
+/* K3: dz[r,m,i] = sum_o ds[r,o] * W[m,o,i]  (+ dz if accumulate). workspace: fp32,
+ * at least vcm_basis_bwd_dz_workspace() elements (the tensor-core kernel stages
+ * the stacked bases Wt[M*I, O] there); may be NULL when that returns 0. */
+VCM_API size_t vcm_basis_bwd_dz_workspace(int64_t rows, int M, int I, int O, int precision);
+VCM_API int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, float *workspace, int64_t rows, int M,
+                             int I, int O, int accumulate, int precision, void *stream);
 
 /* K4: dW[m,o,i] = sum_r ds[r,o] * z[r,m,i]. workspace: fp32, at least
  * vcm_basis_bwd_dw_workspace() elements. Deterministic split reduction. */

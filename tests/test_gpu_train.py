@@ -29,7 +29,7 @@ def test_fused_adam_matches_torch():
 
 def _small_model(seed=0):
     from vcmeshconv_b200 import graph_sampling, synthetic
-    pts, faces = synthetic.sphere(600, seed=seed)
+    pts, faces = synthetic.sphere(600, seed=0)          # same template, `seed` only varies the weights
     tabs, nums = graph_sampling.build_tables(faces, 600, synthetic.alternating_levels(5))
     enc = [tabs["pool%d" % l] for l in range(1, 4)]
     dec = [tabs["unpool%d" % l] for l in range(3, 0, -1)]

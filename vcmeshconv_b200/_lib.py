@@ -43,7 +43,8 @@ SIGNATURES = {
     "vcm_basis_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p]),
     "vcm_act_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p]),
     "vcm_colsum": (_i, [_p, _p, _i, _i, _p]),
-    "vcm_basis_bwd_dz": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, _p]),
+    "vcm_basis_bwd_dz_workspace": (_sz, [_i64, _i, _i, _i, _i]),
+    "vcm_basis_bwd_dz": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p]),
     "vcm_basis_bwd_dw_workspace": (_sz, [_i64, _i, _i, _i, _i]),
     "vcm_basis_bwd_dw": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
     "vcm_adam_step": (_i, [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _i, _f, _p]),

@@ -32,14 +32,23 @@ int vcm_basis_fwd(const float *z, const float *W, const float *bias, int bias_pe
     return simt_basis_fwd(z, W, bias, bias_per_point, res, y_act, out, R, P_out, M, I, O, act, scale_y, scale_res, st);
 }
 
-int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t rows, int M, int I, int O, int accumulate,
-                     int precision, void *stream) {
+size_t vcm_basis_bwd_dz_workspace(int64_t rows, int M, int I, int O, int precision) {
+    if (rows <= 0 || M <= 0 || I <= 0 || O <= 0) return 0;
+    if (precision != VCM_PREC_FP32 && tc_supported(TC_DZ, rows, M, I, O, precision))
+        return tc_basis_bwd_dz_workspace(M, I, O);
+    return 0;
+}
+
+int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, float *workspace, int64_t rows, int M, int I, int O,
+                     int accumulate, int precision, void *stream) {
     if (int e = check_gemm(rows, M, I, O, precision)) return e;
-    VCM_DEVPTR(ds); VCM_DEVPTR(W); VCM_DEVPTR(dz);
+    VCM_DEVPTR(ds); VCM_DEVPTR(W); VCM_DEVPTR(dz); VCM_DEVPTR_OPT(workspace);
     if (rows == 0) return VCM_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision != VCM_PREC_FP32 && tc_supported(TC_DZ, rows, M, I, O, precision))
-        return tc_basis_bwd_dz(ds, W, dz, rows, M, I, O, accumulate, precision, st);
+    if (precision != VCM_PREC_FP32 && !accumulate && tc_supported(TC_DZ, rows, M, I, O, precision)) {
+        VCM_CHECK(workspace != nullptr, "workspace required for the tensor-core dz GEMM");
+        return tc_basis_bwd_dz(ds, W, dz, workspace, rows, M, I, O, accumulate, precision, st);
+    }
     return simt_basis_bwd_dz(ds, W, dz, rows, M, I, O, accumulate, st);
 }
 

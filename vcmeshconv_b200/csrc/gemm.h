@@ -20,8 +20,10 @@ bool tc_supported(int which, int64_t R, int M, int I, int O, int precision);
 int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_point, const float *res, float *y_act,
                  float *out, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr, int precision,
                  cudaStream_t st);
-int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t R, int M, int I, int O, int accumulate,
-                    int precision, cudaStream_t st);
+size_t tc_basis_bwd_dz_workspace(int M, int I, int O);
+int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64_t R, int M, int I, int O,
+                    int accumulate, int precision, cudaStream_t st);
+int reduce_dw_partials(const float *part, float *dW, int K, int O, int I, int n_split, cudaStream_t st);
 size_t tc_basis_bwd_dw_workspace(int64_t R, int M, int I, int O, int precision);
 int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64_t R, int M, int I, int O,
                     int precision, cudaStream_t st);

@@ -12,7 +12,7 @@
 // W is consumed in the reference's native parameter layout [M][O][I]
 // (`weights.view(M, O, I)`, graphVAESSW.py:125): element (k = m*I + i, o) lives
 // at (m*O + o)*I + i, so no transposed copy of the bases is ever made.
-#include "common.cuh"
+#include "gemm.h"
 
 namespace vcm {
 
@@ -316,6 +316,12 @@ int simt_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t R, int
     DzEpilogue epi{dz, K, accumulate};
     dim3 grid((unsigned)ceil_div(R, BM), (unsigned)ceil_div(K, BN));
     gemm_rows_kernel<false, DzEpilogue><<<grid, GT, 0, st>>>(ds, W, R, O, K, I, O, epi);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+int reduce_dw_partials(const float *part, float *dW, int K, int O, int I, int n_split, cudaStream_t st) {
+    reduce_dw_kernel<<<(unsigned)ceil_div((int64_t)K * O, 256), 256, 0, st>>>(part, dW, K, O, I, n_split);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }

@@ -1,20 +1,506 @@
-// tcgen05 / TMEM basis GEMMs (placeholder until the tensor-core kernels land:
-// reports "no kernel" so api.cu routes every shape to the fp32 CUDA-core path).
+// Basis GEMMs on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with
+// fp32 accumulators in TMEM, operands staged by TMA (cp.async.bulk.tensor) into
+// 128-byte-swizzled shared memory through an mbarrier ring.
+//
+//   FWD  out[r,o]   = epi( sum_{m,i} z[r,m,i] W[m,o,i] )        K2  graphVAESSW.py:125-138,161
+//   DZ   dz[r,m,i]  = sum_o ds[r,o] Wt[(m,i),o]                  K3
+//   DW   dW[(m,i),o]= sum_r z[r,(m,i)] ds[r,o]                   K4  (split over r, fixed-order reduce)
+//
+// One CTA computes one 128 x BN accumulator tile (UMMA M = 128, N = BN <= 256,
+// K = 8 per instruction, 4 instructions per 32-float k-block):
+//   warp 0    TMA producer (one lane)      warp 1    tcgen05.mma issuer (one lane)
+//   warp 2    TMEM allocator               warps 4-7 epilogue: tcgen05.ld -> registers
+//                                                    -> bias / ELU / blend -> global
+// Operand layouts
+//   FWD: A = z tile [128 r][32 k] K-major; B = W tile [BN o][32 i] K-major, cut out
+//        of the reference's native [M][O][I] parameter by a 3-D tensor map
+//        (i, o, m) - the stacked-basis matrix is never materialised for K2;
+//   DZ : A = ds tile [128 r][32 o] K-major; B = Wt tile [BN k][32 o] K-major from the
+//        transposed bases Wt[K][O] (a few MB, rebuilt per call by transpose_kernel);
+//   DW : the reduction index r is the slow index of both z and ds, so both
+//        operands are MN-major: 3-D tensor maps (32 contiguous, r, block) drop
+//        [blk][32 r][32] boxes that are exactly the canonical MN-major SW128 layout.
+// Shapes need I % 32 == 0 and O % 32 == 0; everything else (I = 3, O = 3) stays on
+// the CUDA-core kernels of gemm_simt.cu.
+#include <cuda.h>
+
 #include "gemm.h"
 
 namespace vcm {
+namespace {
 
-bool tc_supported(int, int64_t, int, int, int, int) { return false; }
-int tc_basis_fwd(const float *, const float *, const float *, int, const float *, float *, float *, int64_t, int, int,
-                 int, int, int, float, float, int, cudaStream_t) {
-    return fail(VCM_EUNSUPPORTED, "tensor-core forward GEMM not built");
+constexpr int TM = 128;           // accumulator rows per CTA (UMMA M)
+constexpr int TK = 32;            // fp32 per k-block: one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TM * TK * 4;          // 16 KB
+constexpr int NTHREADS = 256;
+
+enum { MODE_FWD = 0, MODE_DZ = 1, MODE_DW = 2 };
+
+struct TcParams {
+    // problem
+    int64_t R;          // rows of the row-major activations
+    int K, O, I;        // K = M*I
+    int P_out;
+    int num_kb;         // k-blocks of the whole reduction
+    int kb_per_m;       // FWD: I/32 (k-blocks per basis), otherwise num_kb
+    int kb_per_split;   // DW: k-blocks per CTA along r; otherwise num_kb
+    // epilogue
+    const float *bias;
+    const float *res;
+    float *y_act;
+    float *out;         // FWD: out; DZ: dz; DW: partial [split][K][O]
+    int per_point, act;
+    float sy, sr;
+};
+
+// ---------------------------------------------------------------- PTX wrappers --
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-int tc_basis_bwd_dz(const float *, const float *, float *, int64_t, int, int, int, int, int, cudaStream_t) {
-    return fail(VCM_EUNSUPPORTED, "tensor-core dz GEMM not built");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-size_t tc_basis_bwd_dw_workspace(int64_t, int, int, int, int) { return 0; }
-int tc_basis_bwd_dw(const float *, const float *, float *, float *, int64_t, int, int, int, int, cudaStream_t) {
-    return fail(VCM_EUNSUPPORTED, "tensor-core dW GEMM not built");
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the launch, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s at 2 GHz
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], single-thread issue
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (sm_100 format): start address, leading /
+// stride byte offsets (>> 4), version 1, SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor: D = F32, A = B = TF32, M = 128, N = BN, majors per operand.
+__host__ __device__ constexpr uint32_t make_idesc(int bn, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+__device__ __forceinline__ float elu1(float t) { return t > 0.f ? t : expm1f(t); }
+
+// --------------------------------------------------------------------- kernel --
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    constexpr int B_BYTES = BN * TK * 4;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms (8 rows x 128 B)
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *acc_full = empty + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y, split = blockIdx.z;
+    const int kb_begin = MODE == MODE_DW ? split * p.kb_per_split : 0;
+    const int kb_end = MODE == MODE_DW ? min(kb_begin + p.kb_per_split, p.num_kb) : p.num_kb;
+    const int n_iter = kb_end - kb_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+            const int kb = kb_begin + it;
+            if (MODE == MODE_DW) {
+                // A: z  as (32 kz, r, kz-block): box (32, 32 r, 4 blocks)   -> [4][32 r][32]
+                // B: ds as (32 o,  r, o-block) : box (32, 32 r, BN/32)      -> [BN/32][32 r][32]
+                tma_load_3d(a_dst, &map_a, &full[s], 0, kb * TK, m_tile * (TM / 32));
+                tma_load_3d(b_dst, &map_b, &full[s], 0, kb * TK, n_tile * (BN / 32));
+            } else {
+                // A: row-major activations [R][Kred]: box (32 k, 128 r)
+                tma_load_2d(a_dst, &map_a, &full[s], kb * TK, m_tile * TM);
+                // B: (inner 32, rows, basis): FWD cuts W[m][o][i]; DZ reads Wt[k][o] with one "basis"
+                const int m = kb / p.kb_per_m;
+                tma_load_3d(b_dst, &map_b, &full[s], (kb - m * p.kb_per_m) * TK, n_tile * BN, m);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc(BN, MODE == MODE_DW, MODE == MODE_DW);
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a_base = smem_base + s * STAGE_BYTES, b_base = a_base + A_BYTES;
+#pragma unroll
+            for (int j = 0; j < TK / 8; ++j) {
+                uint64_t da, db;
+                if (MODE == MODE_DW) {
+                    // MN-major SW128: 32-element MN blocks 4096 B apart (LBO), 8-row k groups 1024 B apart (SBO)
+                    da = make_desc(a_base + j * 1024, 4096, 1024);
+                    db = make_desc(b_base + j * 1024, 4096, 1024);
+                } else {
+                    // K-major SW128: 8-row groups 1024 B apart (SBO); k advances 32 B inside the swizzle row
+                    da = make_desc(a_base + j * 32, 16, 1024);
+                    db = make_desc(b_base + j * 32, 16, 1024);
+                }
+                umma_tf32(tmem_base, da, db, idesc, (it > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+        }
+        umma_commit(acc_full);                 // accumulator complete
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int q = warp - 4;                // TMEM lane quarter of this warp
+        const int row = q * 32 + lane;         // accumulator row owned by this thread
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        if (n_iter <= 0) {
+            // nothing was accumulated (empty split): contribute zeros
+        }
+        const int64_t gr = (int64_t)m_tile * TM + row;          // FWD/DZ: activation row; DW: kz
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            const int col0 = n_tile * BN + c * 32;
+            if (MODE == MODE_FWD) {
+                if (gr < p.R && col0 < p.O) {
+                    const size_t at = (size_t)gr * p.O + col0;
+                    const float *bp = p.bias ? p.bias + (p.per_point ? (size_t)(gr % p.P_out) * p.O : 0) + col0 : nullptr;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float t[4] = {v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]};
+                        if (bp) {
+                            const float4 b = ldg4(bp + 4 * j4);
+                            t[0] += b.x; t[1] += b.y; t[2] += b.z; t[3] += b.w;
+                        }
+                        if (p.act) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) t[e] = elu1(t[e]);
+                        }
+                        if (p.y_act) st4(p.y_act + at + 4 * j4, make_float4(t[0], t[1], t[2], t[3]));
+                        float4 o = make_float4(t[0] * p.sy, t[1] * p.sy, t[2] * p.sy, t[3] * p.sy);
+                        if (p.res) {
+                            const float4 rr = ldg4(p.res + at + 4 * j4);
+                            o.x = fmaf(rr.x, p.sr, o.x); o.y = fmaf(rr.y, p.sr, o.y);
+                            o.z = fmaf(rr.z, p.sr, o.z); o.w = fmaf(rr.w, p.sr, o.w);
+                        }
+                        st4(p.out + at + 4 * j4, o);
+                    }
+                }
+            } else if (MODE == MODE_DZ) {
+                if (gr < p.R && col0 < p.K) {                   // K % 32 == 0: whole chunk in range
+                    float *dst = p.out + (size_t)gr * p.K + col0;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        st4(dst + 4 * j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+                }
+            } else {
+                if (gr < p.K && col0 < p.O) {
+                    float *dst = p.out + ((size_t)split * p.K + gr) * p.O + col0;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 o = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                        if (n_iter <= 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        st4(dst + 4 * j4, o);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// Wt[k = m*I + i][o] = W[m][o][i]  (the stacked bases [M*I, O] of the north_star)
+__global__ void transpose_bases_kernel(const float *__restrict__ W, float *__restrict__ Wt, int M, int I, int O) {
+    __shared__ float tile[32][33];
+    const int m = blockIdx.z, i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int o = o0 + r, i = i0 + tx;
+        tile[r][tx] = (o < O && i < I) ? __ldg(W + ((size_t)m * O + o) * I + i) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, o = o0 + tx;
+        if (i < I && o < O) Wt[((size_t)m * I + i) * O + o] = tile[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------ host side --
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// fp32 tensor map, 128-byte swizzle, zero fill out of bounds. dims/strides innermost first;
+// strides[0] is implicit (4 bytes).
+int make_map(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+             const uint32_t *box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(VCM_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gd[3], gs[2];
+    cuuint32_t bx[3], es[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 1; i < rank; ++i) gs[i - 1] = strides_bytes[i];
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx,
+                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VCM_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return VCM_OK;
+}
+
+int pick_bn(int n) {       // n % 32 == 0
+    if (n >= 256) return 256;
+    if (n > 64) return 128;
+    if (n > 32) return 64;
+    return 32;
+}
+
+template <int MODE>
+int launch(int bn, dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, cudaStream_t st) {
+#define VCM_TC_CASE(BN_)                                                                                          \
+    case BN_: {                                                                                                   \
+        auto k = tc_gemm_kernel<BN_, MODE>;                                                                       \
+        const int smem = STAGES * (A_BYTES + BN_ * TK * 4) + 1024 + 256;                                          \
+        VCM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
+        k<<<grid, NTHREADS, smem, st>>>(ma, mb, p);                                                               \
+        break;                                                                                                    \
+    }
+    switch (bn) {
+        VCM_TC_CASE(32)
+        VCM_TC_CASE(64)
+        VCM_TC_CASE(128)
+        VCM_TC_CASE(256)
+        default: return fail(VCM_EUNSUPPORTED, "no tensor-core tile of width %d", bn);
+    }
+#undef VCM_TC_CASE
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+struct DwSplit { int n_split, kb_per_split, num_kb; };
+DwSplit plan_dw_tc(int64_t R, int K, int O) {
+    DwSplit s;
+    s.num_kb = (int)ceil_div(R, TK);
+    const int64_t tiles = ceil_div(K, TM) * ceil_div(O, pick_bn(O));
+    int64_t split = ceil_div(2 * (int64_t)sm_count(), tiles);
+    if (split > s.num_kb) split = s.num_kb;
+    if (split < 1) split = 1;
+    s.kb_per_split = (int)ceil_div(s.num_kb, split);
+    s.n_split = (int)ceil_div(s.num_kb, s.kb_per_split);
+    return s;
+}
+
+}  // namespace
+
+bool tc_supported(int which, int64_t R, int M, int I, int O, int precision) {
+    if (precision != VCM_PREC_TF32) return false;           // TF32X3 not built yet: stays on fp32 CUDA cores
+    if (I % 32 != 0 || O % 32 != 0) return false;
+    if (R < 1 || R >= ((int64_t)1 << 31)) return false;
+    (void)which; (void)M;
+    return encode_fn() != nullptr;
+}
+
+int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_point, const float *res, float *y_act,
+                 float *out, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr, int precision,
+                 cudaStream_t st) {
+    (void)precision;
+    const int K = M * I, bn = pick_bn(O);
+    CUtensorMap ma, mb;
+    {
+        const uint64_t d[2] = {(uint64_t)K, (uint64_t)R}, s[2] = {4, (uint64_t)K * 4};
+        const uint32_t b[2] = {TK, TM};
+        if (int e = make_map(&ma, z, 2, d, s, b)) return e;
+    }
+    {
+        const uint64_t d[3] = {(uint64_t)I, (uint64_t)O, (uint64_t)M}, s[3] = {4, (uint64_t)I * 4, (uint64_t)O * I * 4};
+        const uint32_t b[3] = {TK, (uint32_t)bn, 1};
+        if (int e = make_map(&mb, W, 3, d, s, b)) return e;
+    }
+    TcParams p{};
+    p.R = R; p.K = K; p.O = O; p.I = I; p.P_out = P_out;
+    p.num_kb = K / TK; p.kb_per_m = I / TK; p.kb_per_split = p.num_kb;
+    p.bias = bias; p.res = res; p.y_act = y_act; p.out = out; p.per_point = per_point; p.act = act; p.sy = sy; p.sr = sr;
+    dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(O, bn), 1);
+    return launch<MODE_FWD>(bn, grid, ma, mb, p, st);
+}
+
+size_t tc_basis_bwd_dz_workspace(int M, int I, int O) { return (size_t)M * I * O; }
+
+int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64_t R, int M, int I, int O,
+                    int accumulate, int precision, cudaStream_t st) {
+    (void)precision;
+    if (accumulate) return fail(VCM_EUNSUPPORTED, "tensor-core dz does not accumulate");
+    const int K = M * I, bn = pick_bn(K);
+    // stacked bases Wt[K][O]
+    dim3 tg((unsigned)ceil_div(I, 32), (unsigned)ceil_div(O, 32), (unsigned)M);
+    transpose_bases_kernel<<<tg, 256, 0, st>>>(W, ws, M, I, O);
+    VCM_LAUNCH_CHECK();
+    CUtensorMap ma, mb;
+    {
+        const uint64_t d[2] = {(uint64_t)O, (uint64_t)R}, s[2] = {4, (uint64_t)O * 4};
+        const uint32_t b[2] = {TK, TM};
+        if (int e = make_map(&ma, ds, 2, d, s, b)) return e;
+    }
+    {
+        const uint64_t d[3] = {(uint64_t)O, (uint64_t)K, 1}, s[3] = {4, (uint64_t)O * 4, (uint64_t)K * O * 4};
+        const uint32_t b[3] = {TK, (uint32_t)bn, 1};
+        if (int e = make_map(&mb, ws, 3, d, s, b)) return e;
+    }
+    TcParams p{};
+    p.R = R; p.K = K; p.O = O; p.I = I;
+    p.num_kb = O / TK; p.kb_per_m = p.num_kb; p.kb_per_split = p.num_kb;
+    p.out = dz;
+    dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(K, bn), 1);
+    return launch<MODE_DZ>(bn, grid, ma, mb, p, st);
+}
+
+size_t tc_basis_bwd_dw_workspace(int64_t R, int M, int I, int O, int precision) {
+    (void)precision;
+    const DwSplit s = plan_dw_tc(R, M * I, O);
+    return (size_t)s.n_split * M * I * O;
+}
+
+int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64_t R, int M, int I, int O,
+                    int precision, cudaStream_t st) {
+    (void)precision;
+    const int K = M * I, bn = pick_bn(O);
+    const DwSplit sp = plan_dw_tc(R, K, O);
+    CUtensorMap ma, mb;
+    {
+        const uint64_t d[3] = {32, (uint64_t)R, (uint64_t)(K / 32)}, s[3] = {4, (uint64_t)K * 4, 128};
+        const uint32_t b[3] = {32, TK, TM / 32};
+        if (int e = make_map(&ma, z, 3, d, s, b)) return e;
+    }
+    {
+        const uint64_t d[3] = {32, (uint64_t)R, (uint64_t)(O / 32)}, s[3] = {4, (uint64_t)O * 4, 128};
+        const uint32_t b[3] = {32, TK, (uint32_t)(bn / 32)};
+        if (int e = make_map(&mb, ds, 3, d, s, b)) return e;
+    }
+    TcParams p{};
+    p.R = R; p.K = K; p.O = O; p.I = I;
+    p.num_kb = sp.num_kb; p.kb_per_m = sp.num_kb; p.kb_per_split = sp.kb_per_split;
+    p.out = ws;
+    dim3 grid((unsigned)ceil_div(K, TM), (unsigned)ceil_div(O, bn), (unsigned)sp.n_split);
+    if (int e = launch<MODE_DW>(bn, grid, ma, mb, p, st)) return e;
+    return reduce_dw_partials(ws, dW, K, O, I, sp.n_split, st);
 }
 
 }  // namespace vcm

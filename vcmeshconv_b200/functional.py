@@ -167,7 +167,9 @@ class _BasisGemm(torch.autograd.Function):
         dz = dW = None
         if need_dz:
             dz = torch.empty_like(z)
-            _lib.call("vcm_basis_bwd_dz", _ptr(ds), _ptr(W), _ptr(dz), R, M, I, O, 0, precision, st,
+            n_ws = L.vcm_basis_bwd_dz_workspace(R, M, I, O, precision)
+            ws = torch.empty(n_ws, device=dev, dtype=torch.float32) if n_ws else None
+            _lib.call("vcm_basis_bwd_dz", _ptr(ds), _ptr(W), _ptr(dz), _ptr(ws), R, M, I, O, 0, precision, st,
                       nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
         if need_dW:
             dW = torch.empty_like(W)
