@@ -19,10 +19,12 @@
 //        transposed bases Wt[K][O] (a few MB, rebuilt per call by transpose_kernel);
 //   DW : the reduction index r is the slow index of both z and ds, so both
 //        operands are MN-major: 3-D tensor maps (32 contiguous, r, block) drop
-//        [blk][32 r][32] boxes that are exactly the canonical MN-major SW128 layout.
+//        [blk][32 r][32] boxes in TMA's SWIZZLE_128B_ATOM_32B pattern, which is the
+//        SWIZZLE_128B_BASE32B descriptor layout - the one MN-major layout tf32 has.
 // Shapes need I % 32 == 0 and O % 32 == 0; everything else (I = 3, O = 3) stays on
 // the CUDA-core kernels of gemm_simt.cu.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm.h"
 
@@ -144,13 +146,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // Shared-memory matrix descriptor (sm_100 format): start address, leading /
 // stride byte offsets (>> 4), version 1, SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only
+// layout the hardware accepts for MN-major tf32 operands).
+constexpr uint32_t LT_SW128 = 2, LT_SW128_32B = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = LT_SW128) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
@@ -235,9 +241,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < TK / 8; ++j) {
                 uint64_t da, db;
                 if (MODE == MODE_DW) {
-                    // MN-major SW128: 32-element MN blocks 4096 B apart (LBO), 8-row k groups 1024 B apart (SBO)
-                    da = make_desc(a_base + j * 1024, 4096, 1024);
-                    db = make_desc(b_base + j * 1024, 4096, 1024);
+                    // MN-major tf32 only exists as SWIZZLE_128B_BASE32B (32-byte chunks XOR row % 4, written by
+                    // TMA's SWIZZLE_128B_ATOM_32B): 32-element MN blocks 4096 B apart (LBO), 4-row k groups
+                    // 512 B apart (SBO); one K = 8 instruction covers 8 r-rows = 1024 B.
+                    da = make_desc(a_base + j * 1024, 4096, 512, LT_SW128_32B);
+                    db = make_desc(b_base + j * 1024, 4096, 512, LT_SW128_32B);
                 } else {
                     // K-major SW128: 8-row groups 1024 B apart (SBO); k advances 32 B inside the swizzle row
                     da = make_desc(a_base + j * 32, 16, 1024);
@@ -352,7 +360,7 @@ EncodeTiledFn encode_fn() {
 // fp32 tensor map, 128-byte swizzle, zero fill out of bounds. dims/strides innermost first;
 // strides[0] is implicit (4 bytes).
 int make_map(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-             const uint32_t *box) {
+             const uint32_t *box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(VCM_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gd[3], gs[2];
@@ -360,7 +368,7 @@ int make_map(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
     for (int i = 1; i < rank; ++i) gs[i - 1] = strides_bytes[i];
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx,
-                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(VCM_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return VCM_OK;
@@ -412,6 +420,9 @@ DwSplit plan_dw_tc(int64_t R, int K, int O) {
 
 bool tc_supported(int which, int64_t R, int M, int I, int O, int precision) {
     if (precision != VCM_PREC_TF32) return false;           // TF32X3 not built yet: stays on fp32 CUDA cores
+    // bring-up switch: VCM_TC_DISABLE is a bit mask (1 fwd, 2 dz, 4 dW) of GEMMs kept on the CUDA-core kernels
+    static const int disabled = [] { const char *e = getenv("VCM_TC_DISABLE"); return e ? atoi(e) : 0; }();
+    if (disabled & (1 << which)) return false;
     if (I % 32 != 0 || O % 32 != 0) return false;
     if (R < 1 || R >= ((int64_t)1 << 31)) return false;
     (void)which; (void)M;
@@ -487,12 +498,12 @@ int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64
     {
         const uint64_t d[3] = {32, (uint64_t)R, (uint64_t)(K / 32)}, s[3] = {4, (uint64_t)K * 4, 128};
         const uint32_t b[3] = {32, TK, TM / 32};
-        if (int e = make_map(&ma, z, 3, d, s, b)) return e;
+        if (int e = make_map(&ma, z, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
     }
     {
         const uint64_t d[3] = {32, (uint64_t)R, (uint64_t)(O / 32)}, s[3] = {4, (uint64_t)O * 4, 128};
         const uint32_t b[3] = {32, TK, (uint32_t)(bn / 32)};
-        if (int e = make_map(&mb, ds, 3, d, s, b)) return e;
+        if (int e = make_map(&mb, ds, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
     }
     TcParams p{};
     p.R = R; p.K = K; p.O = O; p.I = I;
@@ -504,3 +515,90 @@ int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64
 }
 
 }  // namespace vcm
+
+// ---------------------------------------------------------------------------
+// Bring-up harness (not part of the product path): loads ONE k-block of the dW
+// operands through the production tensor maps, dumps the two shared-memory tiles,
+// issues the four MMAs with caller-chosen descriptor parameters and dumps the
+// accumulator. Lets the MN-major descriptor encoding be probed in one GPU run.
+namespace vcm {
+namespace {
+__global__ void __launch_bounds__(128, 1)
+debug_dw_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float *dump_a,
+                float *dump_b, float *dump_d, int bn, uint32_t idesc, uint32_t lbo, uint32_t sbo, uint32_t jstride,
+                int kb, uint32_t ltype) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + A_BYTES + 256 * TK * 4);
+    uint64_t *done = full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1);
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_dst = smem_u32(smem), b_dst = a_dst + A_BYTES;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(full, A_BYTES + bn * TK * 4);
+        tma_load_3d(a_dst, &map_a, full, 0, kb * TK, 0);
+        tma_load_3d(b_dst, &map_b, full, 0, kb * TK, 0);
+    }
+    mbar_wait(full, 0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < A_BYTES / 4; e += blockDim.x) dump_a[e] = reinterpret_cast<float *>(smem)[e];
+    for (int e = threadIdx.x; e < bn * TK; e += blockDim.x) dump_b[e] = reinterpret_cast<float *>(smem + A_BYTES)[e];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc_fence_after();
+        for (int j = 0; j < 4; ++j)
+            umma_tf32(tmem_base, make_desc(a_dst + j * jstride, lbo, sbo, ltype),
+                      make_desc(b_dst + j * jstride, lbo, sbo, ltype), idesc, j > 0 ? 1u : 0u);
+        umma_commit(done);
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int c = 0; c < bn / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        for (int i = 0; i < 32; ++i) dump_d[(size_t)(warp * 32 + lane) * bn + c * 32 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+}  // namespace
+}  // namespace vcm
+
+extern "C" VCM_API int vcm_debug_dw_stage(const float *ds, const float *z, float *dump_a, float *dump_b, float *dump_d,
+                                          int64_t R, int K, int O, int a_mn, int b_mn, int lbo, int sbo, int jstride,
+                                          int kb, int tma_swz32, int ltype, void *stream) {
+    using namespace vcm;
+    const int bn = pick_bn(O);
+    CUtensorMap ma, mb;
+    {
+        const uint64_t d[3] = {32, (uint64_t)R, (uint64_t)(K / 32)}, s[3] = {4, (uint64_t)K * 4, 128};
+        const uint32_t b[3] = {32, TK, TM / 32};
+        if (int e = make_map(&ma, z, 3, d, s, b, tma_swz32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
+    {
+        const uint64_t d[3] = {32, (uint64_t)R, (uint64_t)(O / 32)}, s[3] = {4, (uint64_t)O * 4, 128};
+        const uint32_t b[3] = {32, TK, (uint32_t)(bn / 32)};
+        if (int e = make_map(&mb, ds, 3, d, s, b, tma_swz32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
+    const int smem = A_BYTES + 256 * TK * 4 + 1024 + 256;
+    VCM_CUDA(cudaFuncSetAttribute(debug_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    debug_dw_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(ma, mb, dump_a, dump_b, dump_d, bn,
+                                                            make_idesc(bn, a_mn, b_mn), lbo, sbo, jstride, kb, (uint32_t)ltype);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
