@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--vertices", type=int, default=N_VERT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
 
@@ -213,11 +214,14 @@ def run_ours(args):
         barrier()
         t1 = time.time()
         ms = e0.elapsed_time(e1)
+        n_launch = _lib.lib().vcm_launch_count() - l0
+        if trainer._graph is not None:
+            n_launch = trainer.graph_launches * steps              # replayed, not re-issued from the host
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
-        return ms, _lib.lib().vcm_launch_count() - l0, t0, t1
+        return ms, n_launch, t0, t1
 
     def step_resident(i):
         pc, nor = resident[i % n_rot]
@@ -230,11 +234,15 @@ def run_ours(args):
 
     def step_e2e(i):
         hp, hn = pin[i % n_rot]
-        dev_pc.copy_(hp, non_blocking=True)
-        dev_nor.copy_(hn, non_blocking=True)
-        loss, _ = trainer.step(dev_pc, dev_nor)
+        tp = trainer.static_pc if trainer._graph is not None else dev_pc
+        tn = trainer.static_nor if trainer._graph is not None else dev_nor
+        tp.copy_(hp, non_blocking=True)                            # pinned host -> device, inside the timed region
+        tn.copy_(hn, non_blocking=True)
+        loss, _ = trainer.step(tp, tn)
         loss_host.copy_(loss.reshape(1), non_blocking=False)       # device -> host read of the step's result
 
+    if not args.no_graph:
+        trainer.capture(resident[0][0], resident[0][1], warmup=2)
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -250,7 +258,10 @@ def run_ours(args):
 
     roof, breakdown = None, None
     if rank == 0 and not args.no_profile:
+        # per-kernel events need eager launches: same kernels, same stream, launched one by one
+        g, trainer._graph = trainer._graph, None
         roof, breakdown = roofline(trainer, resident, n_rot, min(args.steps, 5))
+        trainer._graph = g
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cms, cores = cpu_reference_run(args, args.cpu_steps, 1, tabs, pts, faces)
@@ -263,7 +274,8 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": gbatch, "vertices": args.vertices,
-                       "parallelism": "dp%d" % world, "gemm_precision": precision, "trainable_params": n_params,
+                       "parallelism": "dp%d" % world, "gemm_precision": precision,
+                       "launch": "eager" if args.no_graph else "cuda-graph replay of the whole step", "trainable_params": n_params,
                        "point_nums": nums, "l2": "inputs rotate over %d batches; each step streams GBs of "
                        "intermediates (>> 126 MB L2), nothing survives in L2 between steps" % n_rot},
             "e2e": {"value": e2e, "unit": "meshes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -296,7 +308,12 @@ def roofline(trainer, resident, n_rot, steps):
     total = sum(v["ms"] for v in summ.values())
     breakdown = {k: {"ms_per_step": v["ms"] / steps, "share": v["ms"] / total, "calls_per_step": v["calls"] / steps,
                      "GBps": v["bytes"] / v["ms"] / 1e6 if v["ms"] else None,
-                     "TFLOPs": v["flops"] / v["ms"] / 1e9 if v["ms"] else None} for k, v in summ.items()}
+                     "TFLOPs": v["flops"] / v["ms"] / 1e9 if v["ms"] else None,
+                     "top": [{"shape": t, "ms_per_step": tv["ms"] / steps,
+                              "GBps": tv["bytes"] / tv["ms"] / 1e6 if tv["ms"] else None,
+                              "TFLOPs": tv["flops"] / tv["ms"] / 1e9 if tv["ms"] else None}
+                             for t, tv in sorted(v["by_tag"].items(), key=lambda kv: -kv[1]["ms"])[:4]]}
+                 for k, v in summ.items()}
     top = max(summ, key=lambda k: summ[k]["ms"])
     v = summ[top]
     achieved = v["bytes"] / v["ms"] / 1e6                      # GB/s

@@ -110,7 +110,8 @@ VCM_API int vcm_gather_contract_fwd(const vcm_tables *t, const float *x, const f
  *   dA[p,n,m]   = sum_{b,i} dz[b,p,m,i] * x[b, idx[p,n], i]     (0 on padding)
  *   dG[b,p,n,i] = sum_m A[p,n,m] * dz[b,p,m,i]                  (real edges only)
  * dG is [B,P_out,N,I]; padding slots are left untouched and never read. dG may
- * be NULL when the input gradient is not needed (first layer).
+ * be NULL when the input gradient is not needed (first layer), dA may be NULL
+ * when the coefficients are constants (Laplacian / face gathers of the losses).
  * workspace: fp32, at least vcm_coeff_grad_workspace() elements (may be NULL
  * when that returns 0). Deterministic: fixed reduction order, no atomics. */
 VCM_API size_t vcm_coeff_grad_workspace(const vcm_tables *t, int B, int I, int M);
@@ -171,6 +172,14 @@ VCM_API int vcm_basis_bwd_dw(const float *ds, const float *z, float *dW, float *
  * the reference's SUM-over-replicas semantics). */
 VCM_API int vcm_adam_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1,
                           float beta2, float eps, int step, float grad_scale, void *stream);
+
+/* Same update with the step counter and learning rate resident on the device, so
+ * the call can be captured once in a CUDA graph and replayed: state is 4 floats
+ * {step, lr, 1-beta1^step, sqrt(1-beta2^step)}; the call increments step first.
+ * The host changes the learning rate (ExponentialLR, graphVAE_train.py:281,353)
+ * by writing state[1]. */
+VCM_API int vcm_adam_step_graph(float *p, const float *g, float *m, float *v, size_t n, float *state, float beta1,
+                                float beta2, float eps, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }

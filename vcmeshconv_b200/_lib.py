@@ -48,6 +48,7 @@ SIGNATURES = {
     "vcm_basis_bwd_dw_workspace": (_sz, [_i64, _i, _i, _i, _i]),
     "vcm_basis_bwd_dw": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
     "vcm_adam_step": (_i, [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _i, _f, _p]),
+    "vcm_adam_step_graph": (_i, [_p, _p, _p, _p, _sz, _p, _f, _f, _f, _f, _p]),
 }
 
 

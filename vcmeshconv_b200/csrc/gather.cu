@@ -210,7 +210,7 @@ coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ l
             const int q = iv[n];
             if (q == p_in) continue;                    // warp-uniform (same vertex)
             Vec<VEC> gv;
-            if (active) gv.load(xb + (size_t)q * I);
+            if (active && dA_out != nullptr) gv.load(xb + (size_t)q * I);
             else
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) gv.v[j] = 0.f;
@@ -232,25 +232,28 @@ coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ l
                 for (int j = 0; j < VEC; ++j) og.v[j] = fmaf(a[m], d[m][j], og.v[j]);
             if (active && dG != nullptr) og.store(dGr + (size_t)n * I);
 
+            if (dA_out != nullptr) {                     // kernel-uniform: constant coefficients need no dA
             // dA: per-lane partial over the strip, then warp transpose-reduce
-            float vals[32];
+                float vals[32];
 #pragma unroll
-            for (int m = 0; m < 32; ++m) {
-                if (m < MT) {
-                    float s = 0.f;
+                for (int m = 0; m < 32; ++m) {
+                    if (m < MT) {
+                        float s = 0.f;
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) s = fmaf(d[m][j], gv.v[j], s);
-                    vals[m] = s;
-                } else {
-                    vals[m] = 0.f;
+                        for (int j = 0; j < VEC; ++j) s = fmaf(d[m][j], gv.v[j], s);
+                        vals[m] = s;
+                    } else {
+                        vals[m] = 0.f;
+                    }
                 }
+                const float tot = warp_transpose_reduce<MT>(vals, lane);
+                if (lane < MT) pw[n * MT + lane] += tot; // warp-private slot: no race, fixed order
             }
-            const float tot = warp_transpose_reduce<MT>(vals, lane);
-            if (lane < MT) pw[n * MT + lane] += tot;     // warp-private slot: no race, fixed order
         }
     }
     __syncthreads();
 
+    if (dA_out == nullptr) return;
     // cross-warp reduction in fixed warp order; padding slots get exactly 0
     const int warps_per_v = g.CB / 32;
     for (int e = tid; e < g.TP * n_max * M; e += kThreads) {
@@ -421,13 +424,14 @@ static int launch_grad(const Tables *t, const float *dz, const float *x, const f
     auto k = coeff_grad_kernel<MT, VEC>;
     if (int e = set_smem(k, pl.smem)) return e;
     const size_t n_dA = (size_t)t->p_out * t->n_max * M;
-    if (pl.n_split > 1 && ws == nullptr) return fail(VCM_EINVAL, "workspace required (%d splits)", pl.n_split);
-    float *target = pl.n_split > 1 ? ws : dA;
+    if (dA != nullptr && pl.n_split > 1 && ws == nullptr)
+        return fail(VCM_EINVAL, "workspace required (%d splits)", pl.n_split);
+    float *target = dA == nullptr ? nullptr : (pl.n_split > 1 ? ws : dA);
     dim3 grid((unsigned)ceil_div(t->p_out, pl.g.TP), (unsigned)pl.n_split);
     k<<<grid, kThreads, pl.smem, st>>>(t->idx, t->last, t->perm, dz, x, A, target, dG, t->p_in, t->p_out, t->n_max,
                                        I, M, pl.g, pl.passes, pl.n_split);
     VCM_LAUNCH_CHECK();
-    if (pl.n_split > 1) {
+    if (dA != nullptr && pl.n_split > 1) {
         sum_splits_kernel<<<(unsigned)ceil_div((int64_t)n_dA, 256), 256, 0, st>>>(ws, dA, n_dA, pl.n_split);
         VCM_LAUNCH_CHECK();
     }
@@ -497,7 +501,8 @@ int vcm_coeff_grad(const vcm_tables *h, const float *dz, const float *x, const f
                    float *ws, int B, int I, int M, void *stream) {
     const Tables *t = as_tables(h);
     if (int e = check_common(t, B, I, M)) return e;
-    VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
+    VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR_OPT(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
+    VCM_CHECK(dA != nullptr || dG != nullptr, "nothing to compute: dA and dG are both NULL");
     if (t->p_out == 0) return VCM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = I % 4 == 0 && aligned16(x) && aligned16(dz) && (dG == nullptr || aligned16(dG));

@@ -395,6 +395,45 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
 }
 }  // namespace vcm
 
+namespace vcm {
+// Device-resident optimizer state for CUDA-graph replay: state = {step, lr, 1-b1^t, sqrt(1-b2^t)}.
+__global__ void adam_advance_kernel(float *state, float b1, float b2) {
+    const float t = state[0] + 1.f;
+    state[0] = t;
+    state[2] = 1.f - powf(b1, t);
+    state[3] = sqrtf(1.f - powf(b2, t));
+}
+__global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                float *__restrict__ v, size_t n, const float *__restrict__ state, float b1, float b2,
+                                float eps, float grad_scale) {
+    const float lr = state[1], bc1 = state[2], bc2_sqrt = state[3];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * grad_scale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+}
+}  // namespace vcm
+
+extern "C" int vcm_adam_step_graph(float *p, const float *g, float *m, float *v, size_t n, float *state, float beta1,
+                                   float beta2, float eps, float grad_scale, void *stream) {
+    VCM_DEVPTR(p); VCM_DEVPTR(g); VCM_DEVPTR(m); VCM_DEVPTR(v); VCM_DEVPTR(state);
+    cudaStream_t st = (cudaStream_t)stream;
+    vcm::adam_advance_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
+    VCM_LAUNCH_CHECK();
+    if (n == 0) return VCM_OK;
+    int64_t blocks = vcm::ceil_div((int64_t)n, 256 * 4);
+    const int64_t cap = (int64_t)vcm::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    vcm::adam_dev_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, state, beta1, beta2, eps, grad_scale);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
 extern "C" int vcm_adam_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1,
                              float beta2, float eps, int step, float grad_scale, void *stream) {
     VCM_CHECK(step >= 1, "Adam step counter starts at 1");

@@ -76,16 +76,17 @@ class _GatherContract(torch.autograd.Function):
             return (torch.zeros_like(x) if need_dx else None), (torch.zeros_like(A) if need_dA else None), None
         dz = _req(dz, "dz")
         L = _lib.lib()
-        dA = torch.empty_like(A)
+        dA = torch.empty_like(A) if need_dA else None
         dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
-        n_ws = L.vcm_coeff_grad_workspace(t.handle, B, I, M)
+        n_ws = L.vcm_coeff_grad_workspace(t.handle, B, I, M) if need_dA else 0
         ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
         st = _lib.stream_ptr()
         nnz, tag = t.nnz, "P%d>%d I%d M%d" % (p_in, t.p_out, I, M)
         gb = 4 * B * nnz * I
         _lib.call("vcm_coeff_grad", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M, st,
-                  nbytes=4 * (dz.numel() + x.numel() + 2 * nnz * M + nnz) + (gb if need_dx else 0),
-                  flops=(4 if need_dx else 2) * B * nnz * M * I, tag=tag)
+                  nbytes=4 * (dz.numel() + (x.numel() if need_dA else 0) + (2 if need_dA else 1) * nnz * M + nnz) +
+                  (gb if need_dx else 0),
+                  flops=2 * (int(need_dx) + int(need_dA)) * B * nnz * M * I, tag=tag)
         dx = None
         if need_dx:
             dx = torch.empty_like(x)

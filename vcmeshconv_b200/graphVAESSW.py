@@ -228,18 +228,44 @@ class MCVcoeffs(nn.Module):
 
 class MCLoss(nn.Module):
     """Geometric and graph-Laplacian losses over the layer-0 table
-    (graphVAESSW.py:405-575). SURVEY §8(f) N-1: O(B*P*3) work outside the
-    vc-conv hot path; expressed with device-side torch ops (one gather over the
-    whole padded table instead of the reference's Python loop over N)."""
+    (graphVAESSW.py:405-575).
+
+    The reference builds the Laplacian with a Python loop of N advanced-index
+    gathers (whose autograd backward is a sort-based index_put). Here it is ONE
+    launch of the gather/contract kernel (K1) with M = 1 and constant
+    coefficients  L[p,0] = cnt_p, L[p,n>0] = -1  over the same layer-0 table;
+    its backward is the deterministic reverse-CSR scatter (K6). The Laplacian is
+    linear, so the losses apply it to (gt - prediction) once instead of twice."""
 
     def __init__(self, param):
         super().__init__()
-        self.register_buffer("initial_neighbor_id_lstlst", torch.as_tensor(np.asarray(param.neighbor_id_lstlst)).long())
-        self.register_buffer("initial_neighbor_num_lst", torch.as_tensor(np.asarray(param.neighbor_num_lst)).float())
+        ids = np.asarray(param.neighbor_id_lstlst)
+        cnt = np.asarray(param.neighbor_num_lst)
+        self.register_buffer("initial_neighbor_id_lstlst", torch.as_tensor(ids).long())
+        self.register_buffer("initial_neighbor_num_lst", torch.as_tensor(cnt).float())
         self.initial_max_neighbor_num = self.initial_neighbor_id_lstlst.shape[1]
+        n_pt, n_max = ids.shape
+        coef = -np.ones((n_pt, n_max, 1), np.float32)
+        coef[:, 0, 0] = cnt.astype(np.float32)
+        self.register_buffer("_lap_coeffs", torch.from_numpy(coef), persistent=False)
+        table = np.full((n_pt, 1 + 2 * n_max), -1, np.int32)
+        table[:, 0] = cnt
+        table[:, 1::2] = ids
+        self._table_host = table
+        self._tables = {}
 
     def forward(self):
         return
+
+    def _laplacian(self, pc):
+        dev = pc.device
+        if dev.type != "cuda":
+            raise RuntimeError("MCLoss runs on CUDA only (no CPU fallback)")
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        t = self._tables.get(key)
+        if t is None:
+            t = self._tables[key] = DeviceTables(self._table_host, self._table_host.shape[0], torch.device("cuda", key))
+        return F_.gather_contract(pc, self._lap_coeffs, t)          # [B, P, 3]
 
     def compute_geometric_loss_l1(self, gt_pc, predict_pc, weights=[]):
         if len(weights) == 0:
@@ -254,14 +280,6 @@ class MCLoss(nn.Module):
     def compute_geometric_mean_euclidean_dist_error(self, gt_pc, predict_pc, weights=[]):
         d = (gt_pc - predict_pc).pow(2).sum(2).pow(0.5)
         return d.mean() if len(weights) == 0 else (d * weights).sum()
-
-    def _laplacian(self, pc):
-        # cnt_p * x_self - sum of the remaining neighbours; Laplacian is linear, so callers apply it to differences
-        batch, n, c = pc.shape
-        ids = self.initial_neighbor_id_lstlst
-        pad = torch.cat((pc, pc.new_zeros(batch, 1, c)), 1)
-        others = pad[:, ids[:, 1:].reshape(-1)].view(batch, n, ids.shape[1] - 1, c).sum(2)
-        return pad[:, ids[:, 0]] * self.initial_neighbor_num_lst.view(1, n, 1) - others
 
     def compute_laplace_loss_l1(self, gt_pc_raw, predict_pc_raw, weights=[]):
         d = self._laplacian(gt_pc_raw - predict_pc_raw).abs()

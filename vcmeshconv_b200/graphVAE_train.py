@@ -27,6 +27,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import _lib
+from . import functional as F_
 from . import graphVAESSW as vae_model
 
 ENC_CHANNELS = [3, 32, 64, 128, 256, 512, 64]      # graphVAE_train.py:151 (hard-coded there)
@@ -61,7 +62,16 @@ class Net_autoenc(nn.Module):
         self.mcvcoeffsdec = vae_model.MCVcoeffs(self.mcstructuredec, weight_num)
         self.net_geodec = vae_model.MCDec(self.mcstructuredec, dec_channels, weight_num)
         self.net_loss = vae_model.MCLoss(param)
-        self.register_buffer("t_facedata", torch.as_tensor(np.asarray(facedata)).long())
+        faces = np.asarray(facedata).astype(np.int64)
+        self.register_buffer("t_facedata", torch.from_numpy(faces).long())
+        # the three face-corner gathers of the normal loss (graphVAE_train.py:213-217) as ONE gather/contract
+        # launch: a table with one row per face listing its 3 vertices, M = 1, coefficients 1
+        ftab = np.zeros((faces.shape[0], 7), np.int32)
+        ftab[:, 0] = 3
+        ftab[:, 1::2] = faces
+        self._face_table_host = ftab
+        self._face_tables = {}
+        self.register_buffer("_face_coeffs", torch.ones(faces.shape[0], 3, 1), persistent=False)
         self.w_pose = param.w_pose
         self.w_laplace = param.w_laplace
         self.klweight = 1e-5
@@ -78,14 +88,22 @@ class Net_autoenc(nn.Module):
         klloss = torch.mean(-0.5 - t_logstd + 0.5 * t_mu ** 2 + 0.5 * torch.exp(2 * t_logstd))
         out_pc_batch = self.net_geodec(t_z, self.mcvcoeffsdec)[:, :, 0:3]
         dif_pos = out_pc_batch - in_pc_batch
-        f = self.t_facedata
-        tri = dif_pos[:, f[:, 0]] + dif_pos[:, f[:, 1]] + dif_pos[:, f[:, 2]]
+        tri = F_.gather_contract(dif_pos.contiguous(), self._face_coeffs, self._face_tables_on(dif_pos.device))
         loss_normal = (tri / 3.0 * t_nor).sum(2).pow(2).mean()
         loss_pose_l1 = self.net_loss.compute_geometric_loss_l1(in_pc_batch[:, :, 0:3], out_pc_batch)
         loss_laplace = self.net_loss.compute_laplace_loss_l2(in_pc_batch[:, :, 0:3], out_pc_batch)
         loss = (loss_pose_l1 * self.w_pose + loss_laplace * self.w_laplace + klloss * self.klweight +
                 loss_normal * self.w_nor)
         return loss, loss_pose_l1, loss_laplace, klloss, loss_normal, out_pc_batch
+
+    def _face_tables_on(self, device):
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        t = self._face_tables.get(key)
+        if t is None:
+            from .connectivity import DeviceTables
+            t = self._face_tables[key] = DeviceTables(self._face_table_host, self.mcstructureenc.point_num,
+                                                      torch.device("cuda", key))
+        return t
 
     def forward(self, in_pc_batch, iteration=0, frame=None, t_idx=None, t_nor=None, bDebug=False):
         loss, l1, lap, kl, nor, _ = self.losses(in_pc_batch, t_nor)
@@ -155,7 +173,9 @@ class DataParallelTrainer:
         self.flat = FlatBuffers(model.trainable_parameters(), bucket_bytes)
         self.exp_avg = torch.zeros_like(self.flat.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat.flat_p)
-        self.step_count = 0
+        # optimizer scalars live on the device so a captured step can be replayed: {step, lr, 1-b1^t, sqrt(1-b2^t)}
+        self.opt_state = torch.tensor([0.0, lr, 0.0, 0.0], device=self.flat.flat_p.device, dtype=torch.float32)
+        self._graph = None
         self.overlap = overlap and self.world > 1
         self._pending = []
         self._handles = []
@@ -179,6 +199,8 @@ class DataParallelTrainer:
         self._count = list(self._remaining)
         for i, p in enumerate(self.flat.params):
             def hook(param, i=i):
+                if not self.overlap:
+                    return
                 b = owner[i]
                 self._count[b] -= 1
                 if self._count[b] == 0:
@@ -211,28 +233,84 @@ class DataParallelTrainer:
         loss.backward()
         return loss.detach(), (l1.detach(), lap.detach(), kl.detach(), lnor.detach())
 
+    @property
+    def step_count(self):
+        return int(self.opt_state[0].item())
+
+    def set_lr(self, lr):
+        """ExponentialLR of the reference (graphVAE_train.py:281,353) = one scalar write per epoch."""
+        self.lr = lr
+        self.opt_state[1] = lr
+
     def optimizer_step(self):
-        self.step_count += 1
         f = self.flat
-        if f.flat_p.is_cuda:
-            _lib.check(_lib.lib().vcm_adam_step(f.flat_p.data_ptr(), f.flat_g.data_ptr(), self.exp_avg.data_ptr(),
-                                                self.exp_avg_sq.data_ptr(), f.total, self.lr, self.betas[0],
-                                                self.betas[1], self.eps, self.step_count, 1.0, _lib.stream_ptr()))
-        else:
+        if not f.flat_p.is_cuda:
             raise RuntimeError("the optimizer step runs on CUDA only (no CPU fallback)")
+        _lib.call("vcm_adam_step_graph", f.flat_p.data_ptr(), f.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), f.total, self.opt_state.data_ptr(), self.betas[0], self.betas[1],
+                  self.eps, 1.0, _lib.stream_ptr(), nbytes=28 * f.total, flops=12 * f.total)
 
     def step(self, pc, nor, eps=None):
+        if self._graph is not None and eps is None:
+            return self._graph_step(pc, nor)
         loss, parts = self.forward_backward(pc, nor, eps)
         self._finish_reduction()
         self.optimizer_step()
         return loss, parts
+
+    # -- CUDA-graph capture of the step -----------------------------------------------
+    def capture(self, pc, nor, warmup=3):
+        """Captures zero_grad + forward + backward (+ Adam when there is no collective in
+        between) into CUDA graphs; tables and shapes are static, so every later
+        step() is one or two graph launches instead of ~300 kernel launches from
+        Python. With world_size > 1 the gradient all-reduce (NCCL) runs between
+        the two graphs on the same stream."""
+        assert pc.is_cuda and self._graph is None
+        self.overlap = False                         # no NCCL launches inside the capture
+        self.static_pc, self.static_nor = pc.clone(), nor.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.forward_backward(self.static_pc, self.static_nor)
+                self._finish_reduction()
+                self.optimizer_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        l0 = _lib.lib().vcm_launch_count()
+        g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_fb, capture_error_mode="relaxed"):
+            self.static_loss, self.static_parts = self.forward_backward(self.static_pc, self.static_nor)
+            if self.world == 1:
+                self.optimizer_step()
+        g_opt = None
+        if self.world > 1:
+            g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_opt, capture_error_mode="relaxed"):
+                self.optimizer_step()
+        self._graph = (g_fb, g_opt)
+        self.graph_launches = int(_lib.lib().vcm_launch_count() - l0)     # our kernels inside one replayed step
+        return self
+
+    def _graph_step(self, pc, nor):
+        if pc.data_ptr() != self.static_pc.data_ptr():
+            self.static_pc.copy_(pc, non_blocking=True)
+        if nor.data_ptr() != self.static_nor.data_ptr():
+            self.static_nor.copy_(nor, non_blocking=True)
+        g_fb, g_opt = self._graph
+        g_fb.replay()
+        if g_opt is not None:
+            dist.all_reduce(self.flat.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            g_opt.replay()
+        return self.static_loss, self.static_parts
 
     # -- checkpoint layout of the reference (graphVAE_train.py:339-347) ----------
     def state_dict(self):
         m = self.model
         return {"encgeo_state_dict": m.net_geoenc.state_dict(), "decgeo_state_dict": m.net_geodec.state_dict(),
                 "mcvcoeffsdec_dict": m.mcvcoeffsdec.state_dict(), "mcvcoeffsenc_dict": m.mcvcoeffsenc.state_dict(),
-                "optimizer_state_dict": {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}}
+                "optimizer_state_dict": {"step": self.step_count, "lr": self.lr, "exp_avg": self.exp_avg,
+                                         "exp_avg_sq": self.exp_avg_sq}}
 
     def load_model_state(self, ckpt):
         m = self.model
