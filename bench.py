@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--breakdown-file", default="", help="write the full per-kernel, per-shape timing table here")
     return ap.parse_args()
 
 
@@ -260,7 +261,7 @@ def run_ours(args):
     if rank == 0 and not args.no_profile:
         # per-kernel events need eager launches: same kernels, same stream, launched one by one
         g, trainer._graph = trainer._graph, None
-        roof, breakdown = roofline(trainer, resident, n_rot, min(args.steps, 5))
+        roof, breakdown = roofline(trainer, resident, n_rot, min(args.steps, 5), args.breakdown_file)
         trainer._graph = g
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -287,7 +288,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def roofline(trainer, resident, n_rot, steps):
+def roofline(trainer, resident, n_rot, steps, dump=""):
     """Per-entry-point CUDA-event timing of `steps` further training steps
     (events on the launching stream). The dominant entry point's algorithmic
     bytes (SURVEY §8d formulas, counted per call in functional.py) over its
@@ -306,6 +307,14 @@ def roofline(trainer, resident, n_rot, steps):
             trainer.step(pc, nor)
     summ = prof.summary()
     total = sum(v["ms"] for v in summ.values())
+    if dump:
+        with open(dump, "w") as f:
+            for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
+                f.write("%-26s %8.3f ms/step %5.1f%%\n" % (k, v["ms"] / steps, 100 * v["ms"] / total))
+                for t, tv in sorted(v["by_tag"].items(), key=lambda kv: -kv[1]["ms"]):
+                    f.write("    %-30s x%-3d %8.1f us %8.0f GB/s %7.2f TFLOP/s\n" %
+                            (t, tv["calls"] // steps, 1e3 * tv["ms"] / steps, tv["bytes"] / tv["ms"] / 1e6,
+                             tv["flops"] / tv["ms"] / 1e9))
     breakdown = {k: {"ms_per_step": v["ms"] / steps, "share": v["ms"] / total, "calls_per_step": v["calls"] / steps,
                      "GBps": v["bytes"] / v["ms"] / 1e6 if v["ms"] else None,
                      "TFLOPs": v["flops"] / v["ms"] / 1e9 if v["ms"] else None,

@@ -137,10 +137,21 @@ VCM_API int vcm_edge_weights_bwd(const vcm_tables *t, const float *p_nb, const f
  *   y        = act ? ELU(t) : t                (stored to y_act when non-NULL)
  *   out      = y * scale_y + (res ? res * scale_res : 0)
  * rows r = b*P_out + p; bias is [P_out,O] when bias_per_point, [O] otherwise,
- * NULL for none. out may alias nothing else. */
+ * NULL for none. out may alias nothing else. workspace: fp32, at least
+ * vcm_basis_fwd_workspace() elements (partial sums of a split reduction when
+ * there are few rows and a long K); may be NULL when that returns 0. */
+VCM_API size_t vcm_basis_fwd_workspace(int64_t rows, int M, int I, int O, int precision);
 VCM_API int vcm_basis_fwd(const float *z, const float *W, const float *bias, int bias_per_point,
-                          const float *res, float *y_act, float *out, int B, int P_out, int M, int I, int O,
-                          int act, float scale_y, float scale_res, int precision, void *stream);
+                          const float *res, float *y_act, float *out, float *workspace, int B, int P_out, int M,
+                          int I, int O, int act, float scale_y, float scale_res, int precision, void *stream);
+
+/* The K2 epilogue as a stand-alone pass (used when the basis projection runs
+ * before the gather, i.e. for layers whose M*O is narrower than I):
+ *   out = (act ? ELU : id)(s + bias) * scale_y + (res ? res * scale_res : 0)
+ * Its backward is vcm_act_bwd. */
+VCM_API int vcm_bias_act_fwd(const float *s, const float *bias, int bias_per_point, const float *res,
+                             float *y_act, float *out, int B, int P_out, int O, int act, float scale_y,
+                             float scale_res, void *stream);
 
 /* Activation backward + bias gradient in one pass:
  *   ds[r,o]     = dout[r,o] * scale_y * (act ? (y>0 ? 1 : y+1) : 1)

@@ -38,6 +38,7 @@ SHAPES = [  # R, M, I, O
     (28976, 17, 32, 64),       # enc layer 1 of C2 (16 x 1811 rows)
     (5504, 17, 128, 256),
     (816, 17, 256, 512),       # two N tiles
+    (816, 17, 512, 64),        # few rows, K = 8704: split reduction + second-pass epilogue
     (77, 3, 64, 96),           # rows < one tile, O not a power of two
     (300, 5, 96, 32),
 ]
@@ -55,8 +56,10 @@ def test_forward_gemm(shape):
     res = torch.randn(R, O, device="cuda")
     out = torch.full((R, O), float("nan"), device="cuda")
     y = torch.full((R, O), float("nan"), device="cuda")
+    ws = torch.empty(max(_lib.lib().vcm_basis_fwd_workspace(R, M, I, O, TF32), 1), device="cuda")
     _lib.check(_lib.lib().vcm_basis_fwd(z.data_ptr(), W.data_ptr(), bias.data_ptr(), 1, res.data_ptr(), y.data_ptr(),
-                                        out.data_ptr(), B, P, M, I, O, 1, 0.5, 2.0, TF32, _lib.stream_ptr()))
+                                        out.data_ptr(), ws.data_ptr(), B, P, M, I, O, 1, 0.5, 2.0, TF32,
+                                        _lib.stream_ptr()))
     torch.cuda.synchronize()
     Wk = W.view(M, O, I).permute(0, 2, 1).reshape(M * I, O)
 

@@ -16,19 +16,26 @@ int vcm_basis_uses_tensor_cores(int64_t rows, int M, int I, int O, int precision
     return precision != VCM_PREC_FP32 && tc_supported(TC_FWD, rows, M, I, O, precision) ? 1 : 0;
 }
 
+size_t vcm_basis_fwd_workspace(int64_t rows, int M, int I, int O, int precision) {
+    if (rows <= 0 || M <= 0 || I <= 0 || O <= 0) return 0;
+    if (precision != VCM_PREC_FP32 && tc_supported(TC_FWD, rows, M, I, O, precision))
+        return tc_basis_fwd_workspace(rows, M, I, O);
+    return 0;
+}
+
 int vcm_basis_fwd(const float *z, const float *W, const float *bias, int bias_per_point, const float *res,
-                  float *y_act, float *out, int B, int P_out, int M, int I, int O, int act, float scale_y,
-                  float scale_res, int precision, void *stream) {
+                  float *y_act, float *out, float *workspace, int B, int P_out, int M, int I, int O, int act,
+                  float scale_y, float scale_res, int precision, void *stream) {
     VCM_CHECK(B > 0 && P_out >= 0, "bad batch / vertex count");
     const int64_t R = (int64_t)B * P_out;
     if (int e = check_gemm(R, M, I, O, precision)) return e;
     VCM_DEVPTR(z); VCM_DEVPTR(W); VCM_DEVPTR(out);
-    VCM_DEVPTR_OPT(bias); VCM_DEVPTR_OPT(res); VCM_DEVPTR_OPT(y_act);
+    VCM_DEVPTR_OPT(bias); VCM_DEVPTR_OPT(res); VCM_DEVPTR_OPT(y_act); VCM_DEVPTR_OPT(workspace);
     if (R == 0) return VCM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision != VCM_PREC_FP32 && tc_supported(TC_FWD, R, M, I, O, precision))
-        return tc_basis_fwd(z, W, bias, bias_per_point, res, y_act, out, R, P_out, M, I, O, act, scale_y, scale_res,
-                            precision, st);
+        return tc_basis_fwd(z, W, bias, bias_per_point, res, y_act, out, workspace, R, P_out, M, I, O, act, scale_y,
+                            scale_res, precision, st);
     return simt_basis_fwd(z, W, bias, bias_per_point, res, y_act, out, R, P_out, M, I, O, act, scale_y, scale_res, st);
 }
 

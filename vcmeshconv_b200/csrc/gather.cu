@@ -91,12 +91,17 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx, const int32_t *__res
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[m][j] = 0.f;
 
-#pragma unroll 2
+    // No control flow in the loop body (a sentinel neighbour loads nothing and contributes an exact 0), so
+    // the compiler can hoist the gathers of several neighbours ahead of the FMAs: the kernel is bound by
+    // the latency of these L2 gathers, not by their bandwidth.
+#pragma unroll 4
     for (int n = 0; n < l; ++n) {
         const int q = iv[n];
-        if (q == p_in) continue;
         Vec<VEC> gv;
-        gv.load(xb + (size_t)q * I);
+        if (q != p_in) gv.load(xb + (size_t)q * I);
+        else
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) gv.v[j] = 0.f;
         const float4 *a4 = reinterpret_cast<const float4 *>(Av + n * MP);
         float a[MP];
 #pragma unroll
@@ -128,6 +133,12 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx, const int32_t *__res
 // MT <= 32 instead of 5*MT.
 template <int MT>
 __device__ __forceinline__ float warp_transpose_reduce(float (&vals)[32], int lane) {
+    if (MT == 1) {                               // a single value: plain butterfly sum, every lane gets it
+        float v = vals[0];
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        return v;
+    }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
         const bool upper = (lane & s) != 0;
@@ -144,7 +155,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&vals)[32], int la
 }
 
 template <int MT, int VEC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (MT > 17 ? 1 : 2))
 coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ last,
                   const int32_t *__restrict__ perm, const float *__restrict__ dz, const float *__restrict__ x,
                   const float *__restrict__ A, float *__restrict__ dA_out, float *__restrict__ dG, int p_in,
@@ -206,11 +217,12 @@ coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ l
         }
         float *dGr = dG + (((size_t)b * p_out + p) * n_max) * I + i0;
 
+#pragma unroll 2
         for (int n = 0; n < l; ++n) {
             const int q = iv[n];
-            if (q == p_in) continue;                    // warp-uniform (same vertex)
+            const bool real = q != p_in;                // warp-uniform (same vertex)
             Vec<VEC> gv;
-            if (active && dA_out != nullptr) gv.load(xb + (size_t)q * I);
+            if (active && real && dA_out != nullptr) gv.load(xb + (size_t)q * I);
             else
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) gv.v[j] = 0.f;
@@ -230,7 +242,7 @@ coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ l
             for (int m = 0; m < MT; ++m)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) og.v[j] = fmaf(a[m], d[m][j], og.v[j]);
-            if (active && dG != nullptr) og.store(dGr + (size_t)n * I);
+            if (active && real && dG != nullptr) og.store(dGr + (size_t)n * I);
 
             if (dA_out != nullptr) {                     // kernel-uniform: constant coefficients need no dA
             // dA: per-lane partial over the strip, then warp transpose-reduce

@@ -17,9 +17,10 @@ int simt_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int
 // tcgen05 / TMEM kernels (gemm_tc.cu)
 enum { TC_FWD = 0, TC_DZ = 1, TC_DW = 2 };
 bool tc_supported(int which, int64_t R, int M, int I, int O, int precision);
+size_t tc_basis_fwd_workspace(int64_t R, int M, int I, int O);
 int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_point, const float *res, float *y_act,
-                 float *out, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr, int precision,
-                 cudaStream_t st);
+                 float *out, float *ws, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr,
+                 int precision, cudaStream_t st);
 size_t tc_basis_bwd_dz_workspace(int M, int I, int O);
 int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64_t R, int M, int I, int O,
                     int accumulate, int precision, cudaStream_t st);

@@ -257,6 +257,25 @@ __global__ void act_bwd_kernel(const float *__restrict__ dout, const float *__re
     if (dbias) dbias[e] = sum;
 }
 
+// out = (act ? ELU : id)(s + bias) * sy + res * sr   (epilogue of K2 as a stand-alone pass, used when the
+// basis projection runs BEFORE the gather: graphVAESSW.py:135-138,161)
+__global__ void bias_act_fwd_kernel(const float *__restrict__ s, const float *__restrict__ bias,
+                                    const float *__restrict__ res, float *__restrict__ y_act, float *__restrict__ out,
+                                    size_t n, int P_out, int O, int per_point, int act, float sy, float sr) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float t = __ldg(s + e);
+    if (bias) {
+        const size_t po = (size_t)P_out * O;
+        t += __ldg(bias + (per_point ? e % po : e % O));
+    }
+    const float y = act ? elu1(t) : t;
+    if (y_act) y_act[e] = y;
+    float v = y * sy;
+    if (res) v = fmaf(__ldg(res + e), sr, v);
+    out[e] = v;
+}
+
 // dst[c] = sum_r src[r, c]: one block per 32 columns, fixed-order tree
 __global__ void colsum_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols) {
     __shared__ float red[8][33];
@@ -357,6 +376,18 @@ int vcm_act_bwd(const float *dout, const float *y_act, float *ds, float *dbias, 
     if (P_out == 0) return VCM_OK;
     act_bwd_kernel<<<(unsigned)ceil_div((int64_t)P_out * O, 256), 256, 0, (cudaStream_t)stream>>>(
         dout, y_act, ds, dbias, dres, B, P_out, O, act, scale_y, scale_res);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+int vcm_bias_act_fwd(const float *s, const float *bias, int bias_per_point, const float *res, float *y_act,
+                     float *out, int B, int P_out, int O, int act, float scale_y, float scale_res, void *stream) {
+    VCM_CHECK(B > 0 && P_out >= 0 && O > 0, "bad shape");
+    VCM_DEVPTR(s); VCM_DEVPTR(out); VCM_DEVPTR_OPT(bias); VCM_DEVPTR_OPT(res); VCM_DEVPTR_OPT(y_act);
+    const size_t n = (size_t)B * P_out * O;
+    if (n == 0) return VCM_OK;
+    bias_act_fwd_kernel<<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, (cudaStream_t)stream>>>(
+        s, bias, res, y_act, out, n, P_out, O, bias_per_point, act, scale_y, scale_res);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }

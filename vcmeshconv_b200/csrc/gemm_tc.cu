@@ -54,6 +54,8 @@ struct TcParams {
     float *out;         // FWD: out; DZ: dz; DW: partial [split][K][O]
     int per_point, act;
     float sy, sr;
+    int direct;         // DW with a single split: write dW in the native [M][O][I] layout, no reduce pass
+    float *partial;     // FWD with a split reduction: raw partial sums [split][R][O], epilogue runs afterwards
 };
 
 // ---------------------------------------------------------------- PTX wrappers --
@@ -184,8 +186,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, n_tile = blockIdx.y, split = blockIdx.z;
-    const int kb_begin = MODE == MODE_DW ? split * p.kb_per_split : 0;
-    const int kb_end = MODE == MODE_DW ? min(kb_begin + p.kb_per_split, p.num_kb) : p.num_kb;
+    const int kb_begin = split * p.kb_per_split;            // kb_per_split == num_kb when the reduction is not split
+    const int kb_end = min(kb_begin + p.kb_per_split, p.num_kb);
     const int n_iter = kb_end - kb_begin;
 
     if (threadIdx.x == 0) {
@@ -271,7 +273,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
             const int col0 = n_tile * BN + c * 32;
-            if (MODE == MODE_FWD) {
+            if (MODE == MODE_FWD && p.partial != nullptr) {
+                if (gr < p.R && col0 < p.O) {
+                    float *dst = p.partial + ((size_t)split * p.R + gr) * p.O + col0;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        st4(dst + 4 * j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+                }
+            } else if (MODE == MODE_FWD) {
                 if (gr < p.R && col0 < p.O) {
                     const size_t at = (size_t)gr * p.O + col0;
                     const float *bp = p.bias ? p.bias + (p.per_point ? (size_t)(gr % p.P_out) * p.O : 0) + col0 : nullptr;
@@ -304,7 +313,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         st4(dst + 4 * j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
                 }
             } else {
-                if (gr < p.K && col0 < p.O) {
+                if (p.direct) {
+                    // lanes = consecutive kz = consecutive i of one basis: every store below is one 128-byte line
+                    if (gr < p.K && col0 < p.O) {
+                        const int m = (int)gr / p.I, i = (int)gr - m * p.I;
+                        float *dst = p.out + ((size_t)m * p.O + col0) * p.I + i;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[(size_t)j * p.I] = v[j];
+                    }
+                } else if (gr < p.K && col0 < p.O) {
                     float *dst = p.out + ((size_t)split * p.K + gr) * p.O + col0;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
@@ -322,6 +339,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         tmem_dealloc(tmem_base, BN);
     }
+}
+
+// Second pass of a split-reduction forward GEMM: fixed-order sum of the partials, then the K2 epilogue.
+__global__ void splitk_fwd_epilogue_kernel(const float *__restrict__ part, int n_split, int64_t R, int O, int P_out,
+                                           const float *__restrict__ bias, int per_point,
+                                           const float *__restrict__ res, float *__restrict__ y_act,
+                                           float *__restrict__ out, int act, float sy, float sr) {
+    const size_t e4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const size_t n = (size_t)R * O;
+    if (e4 >= n) return;
+    float4 a = ldg4(part + e4);
+    for (int k = 1; k < n_split; ++k) {
+        const float4 b = ldg4(part + (size_t)k * n + e4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float t[4] = {a.x, a.y, a.z, a.w};
+    if (bias) {
+        const size_t r = e4 / O;
+        const int o = (int)(e4 - r * O);
+        const float4 b = ldg4(bias + (per_point ? (size_t)(r % P_out) * O : 0) + o);
+        t[0] += b.x; t[1] += b.y; t[2] += b.z; t[3] += b.w;
+    }
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = elu1(t[i]);
+    }
+    if (y_act) st4(y_act + e4, make_float4(t[0], t[1], t[2], t[3]));
+    float4 o4 = make_float4(t[0] * sy, t[1] * sy, t[2] * sy, t[3] * sy);
+    if (res) {
+        const float4 rr = ldg4(res + e4);
+        o4.x = fmaf(rr.x, sr, o4.x); o4.y = fmaf(rr.y, sr, o4.y); o4.z = fmaf(rr.z, sr, o4.z); o4.w = fmaf(rr.w, sr, o4.w);
+    }
+    st4(out + e4, o4);
 }
 
 // Wt[k = m*I + i][o] = W[m][o][i]  (the stacked bases [M*I, O] of the north_star)
@@ -408,8 +458,10 @@ DwSplit plan_dw_tc(int64_t R, int K, int O) {
     DwSplit s;
     s.num_kb = (int)ceil_div(R, TK);
     const int64_t tiles = ceil_div(K, TM) * ceil_div(O, pick_bn(O));
-    int64_t split = ceil_div(2 * (int64_t)sm_count(), tiles);
-    if (split > s.num_kb) split = s.num_kb;
+    // enough output tiles to fill the machine: one pass, written straight into dW. Otherwise split the
+    // row reduction so that ~1.5 waves of CTAs exist (partials are summed in fixed order afterwards).
+    int64_t split = tiles * 10 >= (int64_t)sm_count() * 7 ? 1 : ceil_div(3 * (int64_t)sm_count(), 2 * tiles);
+    if (split > s.num_kb / 2) split = s.num_kb / 2;
     if (split < 1) split = 1;
     s.kb_per_split = (int)ceil_div(s.num_kb, split);
     s.n_split = (int)ceil_div(s.num_kb, s.kb_per_split);
@@ -429,9 +481,25 @@ bool tc_supported(int which, int64_t R, int M, int I, int O, int precision) {
     return encode_fn() != nullptr;
 }
 
+// Few row tiles but a long reduction (the 51-vertex bottleneck layers: 816 rows, K = 8704): split K so
+// that the machine is filled; partial sums go through a second pass that also runs the epilogue.
+static int fwd_splits(int64_t R, int K, int O) {
+    const int64_t tiles = ceil_div(R, TM) * ceil_div(O, pick_bn(O));
+    const int num_kb = K / TK;
+    if (tiles * 2 > sm_count() || num_kb < 16) return 1;
+    int64_t split = ceil_div((int64_t)sm_count(), tiles);
+    if (split > num_kb / 4) split = num_kb / 4;
+    return split < 1 ? 1 : (int)split;
+}
+
+size_t tc_basis_fwd_workspace(int64_t R, int M, int I, int O) {
+    const int s = fwd_splits(R, M * I, O);
+    return s > 1 ? (size_t)s * R * O : 0;
+}
+
 int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_point, const float *res, float *y_act,
-                 float *out, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr, int precision,
-                 cudaStream_t st) {
+                 float *out, float *ws, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr,
+                 int precision, cudaStream_t st) {
     (void)precision;
     const int K = M * I, bn = pick_bn(O);
     CUtensorMap ma, mb;
@@ -447,10 +515,22 @@ int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_poin
     }
     TcParams p{};
     p.R = R; p.K = K; p.O = O; p.I = I; p.P_out = P_out;
-    p.num_kb = K / TK; p.kb_per_m = I / TK; p.kb_per_split = p.num_kb;
+    int n_split = fwd_splits(R, K, O);
+    if (n_split > 1 && ws == nullptr) n_split = 1;
+    p.num_kb = K / TK; p.kb_per_m = I / TK;
+    p.kb_per_split = (int)ceil_div(p.num_kb, n_split);
+    n_split = (int)ceil_div(p.num_kb, p.kb_per_split);
     p.bias = bias; p.res = res; p.y_act = y_act; p.out = out; p.per_point = per_point; p.act = act; p.sy = sy; p.sr = sr;
-    dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(O, bn), 1);
-    return launch<MODE_FWD>(bn, grid, ma, mb, p, st);
+    p.partial = n_split > 1 ? ws : nullptr;
+    dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(O, bn), (unsigned)n_split);
+    if (int e = launch<MODE_FWD>(bn, grid, ma, mb, p, st)) return e;
+    if (n_split > 1) {
+        splitk_fwd_epilogue_kernel<<<(unsigned)ceil_div(R * O / 4, 256), 256, 0, st>>>(ws, n_split, R, O, P_out, bias,
+                                                                                      per_point, res, y_act, out, act,
+                                                                                      sy, sr);
+        VCM_LAUNCH_CHECK();
+    }
+    return VCM_OK;
 }
 
 size_t tc_basis_bwd_dz_workspace(int M, int I, int O) { return (size_t)M * I * O; }
@@ -508,9 +588,11 @@ int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64
     TcParams p{};
     p.R = R; p.K = K; p.O = O; p.I = I;
     p.num_kb = sp.num_kb; p.kb_per_m = sp.num_kb; p.kb_per_split = sp.kb_per_split;
-    p.out = ws;
+    p.direct = sp.n_split == 1;
+    p.out = p.direct ? dW : ws;
     dim3 grid((unsigned)ceil_div(K, TM), (unsigned)ceil_div(O, bn), (unsigned)sp.n_split);
     if (int e = launch<MODE_DW>(bn, grid, ma, mb, p, st)) return e;
+    if (p.direct) return VCM_OK;
     return reduce_dw_partials(ws, dW, K, O, I, sp.n_split, st);
 }
 

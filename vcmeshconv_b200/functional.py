@@ -124,8 +124,10 @@ class _BasisGemm(torch.autograd.Function):
         if B and p_out:
             nb = 4 * (z.numel() + W.numel() + (bias.numel() if bias is not None else 0) + out.numel() +
                       (res.numel() if res is not None else 0) + (y_act.numel() if y_act is not None else 0))
-            _lib.call("vcm_basis_fwd", _ptr(z), _ptr(W), _ptr(bias), per_point, _ptr(res), _ptr(y_act), _ptr(out), B,
-                      p_out, M, I, O, int(act), scale_y, scale_res, precision, _lib.stream_ptr(),
+            n_ws = _lib.lib().vcm_basis_fwd_workspace(B * p_out, M, I, O, precision)
+            ws = torch.empty(n_ws, device=z.device, dtype=torch.float32) if n_ws else None
+            _lib.call("vcm_basis_fwd", _ptr(z), _ptr(W), _ptr(bias), per_point, _ptr(res), _ptr(y_act), _ptr(out),
+                      _ptr(ws), B, p_out, M, I, O, int(act), scale_y, scale_res, precision, _lib.stream_ptr(),
                       nbytes=nb, flops=2 * B * p_out * M * I * O, tag="R%d K%d O%d" % (B * p_out, M * I, O))
         y_saved = (y_act if y_act is not None else out) if act else None
         ctx.save_for_backward(z, W, y_saved)
@@ -181,6 +183,54 @@ class _BasisGemm(torch.autograd.Function):
         return (dz, dW, dbias, dres) + (None,) * 7
 
 
+class _BiasAct(torch.autograd.Function):
+    """out = (act ? ELU : id)(s + bias) * scale_y + res * scale_res, the K2 epilogue on its own."""
+
+    @staticmethod
+    def forward(ctx, s, bias, res, act, scale_y, scale_res):
+        s = _req(s, "s")
+        B, p_out, O = s.shape
+        per_point = 0
+        if bias is not None:
+            bias = _req(bias, "bias")
+            per_point = 1 if bias.dim() == 2 else 0
+            if tuple(bias.shape) not in ((p_out, O), (O,)):
+                raise RuntimeError("bias must be [%d, %d] or [%d]" % (p_out, O, O))
+        if res is not None:
+            res = _req(res, "residual")
+            if tuple(res.shape) != tuple(s.shape):
+                raise RuntimeError("residual shape mismatch")
+        out = torch.empty_like(s)
+        y_act = torch.empty_like(s) if act and (res is not None or scale_y != 1.0) else None
+        if s.numel():
+            _lib.call("vcm_bias_act_fwd", _ptr(s), _ptr(bias), per_point, _ptr(res), _ptr(y_act), _ptr(out), B, p_out,
+                      O, int(act), scale_y, scale_res, _lib.stream_ptr(), nbytes=4 * s.numel() * 3, flops=4 * s.numel(),
+                      tag="R%d O%d" % (B * p_out, O))
+        ctx.save_for_backward((y_act if y_act is not None else out) if act else None)
+        ctx.cfg = (int(act), scale_y, scale_res, per_point, bias is not None, res is not None, O)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (y,) = ctx.saved_tensors
+        act, sy, sr, per_point, has_bias, has_res, O = ctx.cfg
+        dout = _req(dout, "dout")
+        B, p_out, _ = dout.shape
+        need_db = has_bias and ctx.needs_input_grad[1]
+        need_dres = has_res and ctx.needs_input_grad[2]
+        ds = torch.empty_like(dout)
+        db_pp = torch.empty(p_out, O, device=dout.device, dtype=torch.float32) if need_db else None
+        dres = torch.empty_like(dout) if need_dres else None
+        st = _lib.stream_ptr()
+        _lib.call("vcm_act_bwd", _ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st,
+                  nbytes=4 * dout.numel() * 3, flops=2 * dout.numel(), tag="R%d O%d" % (B * p_out, O))
+        dbias = db_pp
+        if need_db and not per_point:
+            dbias = torch.empty(O, device=dout.device, dtype=torch.float32)
+            _lib.call("vcm_colsum", _ptr(db_pp), _ptr(dbias), p_out, O, st, nbytes=4 * (p_out * O + O), flops=p_out * O)
+        return ds, dbias, dres, None, None, None
+
+
 class _EdgeWeights(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p_nb, tables):
@@ -213,6 +263,10 @@ def basis_gemm(z, weights, bias, res, M, I, O, act, scale_y=1.0, scale_res=0.0, 
     """out = (act ? ELU : id)(z @ stacked(weights) + bias) * scale_y + res * scale_res."""
     return _BasisGemm.apply(z, weights, bias, res, M, I, O, bool(act), float(scale_y), float(scale_res),
                             _precision if precision is None else precision)
+
+
+def bias_act(s, bias, res, act, scale_y=1.0, scale_res=0.0):
+    return _BiasAct.apply(s, bias, res, bool(act), float(scale_y), float(scale_res))
 
 
 def edge_weights(p_neighbors, tables):

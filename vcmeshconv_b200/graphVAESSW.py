@@ -55,6 +55,12 @@ class LASMConvssw(nn.Module):
 
         self._table_host = np.ascontiguousarray(table, dtype=np.int32)
         self._tables = {}          # device index -> DeviceTables (not in the state_dict)
+        self._tables_x = {}        # same, for the basis-expanded table of the project-first order
+        # The op is bilinear, so the basis projection may run before the gather:
+        #   y[b,p,:] = sum_{n,m} A[p,n,m] (W_m x[b,idx[p,n],:])
+        # which moves rows of M*O floats instead of materialising z (M*I per output vertex). It wins when
+        # the projected rows are narrow (last decoder layer: 32 -> 3 channels on the full-resolution mesh).
+        self.project_first = weight_num * out_channel <= 2 * in_channel
 
     # -- device tables ---------------------------------------------------------
     def tables(self, device):
@@ -67,6 +73,23 @@ class LASMConvssw(nn.Module):
             t = self._tables[key] = DeviceTables(self._table_host, self.in_point_num, torch.device("cuda", key))
         return t
 
+    def tables_expanded(self, device):
+        """Device tables of the basis-expanded graph: virtual neighbour (n, m) of p is row idx[p,n]*M + m of
+        the projected input viewed as [B, P_in*M, O]; the coefficient tensor A[P_out, N, M] viewed as
+        [P_out, N*M, 1] lines up with it slot for slot."""
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        t = self._tables_x.get(key)
+        if t is None:
+            M, p_in = self.weight_num, self.in_point_num
+            ids = self._table_host[:, 1::2].astype(np.int64)                     # [P_out, N]
+            real = ids != p_in
+            ex = np.where(real[:, :, None], ids[:, :, None] * M + np.arange(M)[None, None, :], p_in * M)
+            tab = np.full((ids.shape[0], 1 + 2 * ids.shape[1] * M), -1, np.int32)
+            tab[:, 0] = real.sum(1) * M
+            tab[:, 1::2] = ex.reshape(ids.shape[0], -1)
+            t = self._tables_x[key] = DeviceTables(tab, p_in * M, torch.device("cuda", key))
+        return t
+
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
         ids = self.neighbor_id_lstlst.detach().cpu().numpy()
@@ -77,7 +100,7 @@ class LASMConvssw(nn.Module):
             t[:, 0] = cnt
             t[:, 1::2] = ids
             self._table_host = t
-            self._tables = {}
+            self._tables, self._tables_x = {}, {}
 
     # -- forward ------------------------------------------------------------------
     def forward(self, in_pc, raw_w_weights, is_final_layer=False, b_max_pool=False):
@@ -85,8 +108,37 @@ class LASMConvssw(nn.Module):
             # the reference's max-pool branch raises TypeError (tuple + tensor, graphVAESSW.py:130-135)
             raise NotImplementedError("b_max_pool is not supported (it is broken in the reference as well)")
         t = self.tables(in_pc.device)
+        if self.project_first:
+            return self._forward_project_first(in_pc, raw_w_weights, is_final_layer)
         z = F_.gather_contract(in_pc, raw_w_weights, t)
         return self.forward_from_z(z, in_pc, is_final_layer)
+
+    def _residual(self, in_pc, t):
+        """graphVAESSW.py:144-159 -> (res or None, scale_y, scale_res)."""
+        if self.residual_rate == 0:
+            return None, 1.0, 0.0
+        sy, sr = F_.blend_scales(self.residual_rate)
+        I, O = self.in_channel, self.out_channel
+        project = (lambda v: F_.basis_gemm(v, self.weight_res, None, None, 1, I, O, False)) if I != O else (lambda v: v)
+        if self.in_point_num == self.out_point_num:
+            return project(in_pc), sy, sr
+        pn = F_.edge_weights(self.p_neighbors, t).unsqueeze(-1)
+        # projection and weighted pooling are both linear and commute: gather on the narrower side
+        # (the reference projects first, graphVAESSW.py:144-159; same result up to fp32 rounding)
+        if I < O:
+            return project(F_.gather_contract(in_pc, pn, t)), sy, sr
+        return F_.gather_contract(project(in_pc), pn, t), sy, sr
+
+    def _forward_project_first(self, in_pc, raw_w_weights, is_final_layer):
+        B = in_pc.shape[0]
+        M, I, O = self.weight_num, self.in_channel, self.out_channel
+        # u[b,q,m,:] = W_m x[b,q,:]: one GEMM with the bases stacked along the output axis ([1][M*O][I] view)
+        u = F_.basis_gemm(in_pc, self.weights.view(1, M * O * I), None, None, 1, I, M * O, False)
+        tx = self.tables_expanded(in_pc.device)
+        s = F_.gather_contract(u.view(B, self.in_point_num * M, O),
+                               raw_w_weights.reshape(self.out_point_num, self.max_neighbor_num * M, 1), tx)
+        res, sy, sr = self._residual(in_pc, self.tables(in_pc.device))
+        return F_.bias_act(s, self.bias, res, not is_final_layer, sy, sr)
 
     def forward_from_z(self, z, in_pc, is_final_layer=False):
         """Stage 2 on an already contracted z (lets two layers that share input,
@@ -94,16 +146,7 @@ class LASMConvssw(nn.Module):
         t = self.tables(in_pc.device)
         M, I, O = self.weight_num, self.in_channel, self.out_channel
         act = not is_final_layer
-        if self.residual_rate == 0:
-            return F_.basis_gemm(z, self.weights, self.bias, None, M, I, O, act)
-        sy, sr = F_.blend_scales(self.residual_rate)
-        xr = in_pc
-        if I != O:
-            xr = F_.basis_gemm(in_pc, self.weight_res, None, None, 1, I, O, False)
-        if self.in_point_num == self.out_point_num:
-            res = xr
-        else:
-            res = F_.gather_contract(xr, F_.edge_weights(self.p_neighbors, t).unsqueeze(-1), t)
+        res, sy, sr = self._residual(in_pc, t)
         return F_.basis_gemm(z, self.weights, self.bias, res, M, I, O, act, sy, sr)
 
     # the reference keeps its original, memory-hungry formulation as `forward2`
