@@ -220,18 +220,18 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const float *__restrict__ 
     }
 }
 
-// dW[m][o][i] = sum_s part[s][k = m*I+i][o], fixed order
+// dW[m][o][i] = sum_s part[s][k = m*I+i][o], fixed order. Threads walk the partial layout (coalesced reads,
+// n_split of them per element); the single write per element goes to dW's native layout.
 __global__ void reduce_dw_kernel(const float *__restrict__ part, float *__restrict__ dW, int K, int O, int I,
                                  int n_split) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into dW's native layout
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into part[s]: k * O + o
     if (e >= (size_t)K * O) return;
-    const int i = (int)(e % I);
-    const size_t mo = e / I;
-    const int o = (int)(mo % O), m = (int)(mo / O);
-    const size_t src = ((size_t)m * I + i) * O + o;
+    const int o = (int)(e % O);
+    const int k = (int)(e / O);
+    const int m = k / I, i = k - m * I;
     float s = 0.f;
-    for (int k = 0; k < n_split; ++k) s += part[(size_t)k * K * O + src];
-    dW[e] = s;
+    for (int j = 0; j < n_split; ++j) s += part[(size_t)j * K * O + e];
+    dW[((size_t)m * O + o) * I + i] = s;
 }
 
 // ds / dbias / dres in one pass; one thread per (p, o), loop over the batch.

@@ -313,22 +313,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         st4(dst + 4 * j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
                 }
             } else {
-                if (p.direct) {
-                    // lanes = consecutive kz = consecutive i of one basis: every store below is one 128-byte line
-                    if (gr < p.K && col0 < p.O) {
-                        const int m = (int)gr / p.I, i = (int)gr - m * p.I;
-                        float *dst = p.out + ((size_t)m * p.O + col0) * p.I + i;
+                // Written in dW's native [M][O][I] layout (lanes = consecutive kz = consecutive i of one basis,
+                // so every store below is one 128-byte line); with a split reduction each split owns one such
+                // slab and sum_partials_kernel adds the slabs in fixed order.
+                if (gr < p.K && col0 < p.O) {
+                    const int m = (int)gr / p.I, i = (int)gr - m * p.I;
+                    float *dst = p.out + (size_t)split * p.K * p.O + ((size_t)m * p.O + col0) * p.I + i;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[(size_t)j * p.I] = v[j];
-                    }
-                } else if (gr < p.K && col0 < p.O) {
-                    float *dst = p.out + ((size_t)split * p.K + gr) * p.O + col0;
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float4 o = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-                        if (n_iter <= 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                        st4(dst + 4 * j4, o);
-                    }
+                    for (int j = 0; j < 32; ++j) dst[(size_t)j * p.I] = n_iter > 0 ? v[j] : 0.f;
                 }
             }
         }
@@ -372,6 +364,17 @@ __global__ void splitk_fwd_epilogue_kernel(const float *__restrict__ part, int n
         o4.x = fmaf(rr.x, sr, o4.x); o4.y = fmaf(rr.y, sr, o4.y); o4.z = fmaf(rr.z, sr, o4.z); o4.w = fmaf(rr.w, sr, o4.w);
     }
     st4(out + e4, o4);
+}
+
+__global__ void sum_partials_kernel(const float *__restrict__ part, float *__restrict__ out, size_t n, int n_split) {
+    const size_t e4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e4 >= n) return;
+    float4 a = ldg4(part + e4);
+    for (int k = 1; k < n_split; ++k) {
+        const float4 b = ldg4(part + (size_t)k * n + e4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    st4(out + e4, a);
 }
 
 // Wt[k = m*I + i][o] = W[m][o][i]  (the stacked bases [M*I, O] of the north_star)
@@ -593,7 +596,10 @@ int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64
     dim3 grid((unsigned)ceil_div(K, TM), (unsigned)ceil_div(O, bn), (unsigned)sp.n_split);
     if (int e = launch<MODE_DW>(bn, grid, ma, mb, p, st)) return e;
     if (p.direct) return VCM_OK;
-    return reduce_dw_partials(ws, dW, K, O, I, sp.n_split, st);
+    const size_t n = (size_t)K * O;
+    sum_partials_kernel<<<(unsigned)ceil_div((int64_t)(n / 4), 256), 256, 0, st>>>(ws, dW, n, sp.n_split);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
 }
 
 }  // namespace vcm

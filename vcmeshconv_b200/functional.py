@@ -45,6 +45,28 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _grad_target(t):
+    """Slice of the trainer's flat gradient buffer registered for parameter `t` (or for the parameter `t`
+    is a whole, order-preserving view of), if this is the first gradient written to it this step. The
+    backward kernels then write there directly and autograd sees no gradient for the input: no temporary,
+    no accumulate kernel, and the buffer NCCL reduces / Adam reads is filled in place."""
+    if t is None:
+        return None
+    base = t._base if t._base is not None else t
+    buf = getattr(base, "_vcm_grad_buf", None)
+    if buf is None or not t.is_contiguous() or t.numel() != base.numel() or getattr(base, "_vcm_grad_written", False):
+        return None
+    base._vcm_grad_written = True
+    return buf.view(t.shape)
+
+
+def begin_step(params):
+    """Called by the trainer before every (captured or eager) backward: each parameter may be written
+    directly once; a second use falls back to autograd accumulation."""
+    for p in params:
+        p._vcm_grad_written = False
+
+
 class _GatherContract(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, A, tables):
@@ -63,6 +85,7 @@ class _GatherContract(torch.autograd.Function):
                       tag="P%d>%d I%d M%d" % (p_in, tables.p_out, I, M))
         ctx.save_for_backward(x, A)
         ctx.tables = tables
+        ctx.dA_target = _grad_target(A) if A.requires_grad else None
         return z
 
     @staticmethod
@@ -76,7 +99,8 @@ class _GatherContract(torch.autograd.Function):
             return (torch.zeros_like(x) if need_dx else None), (torch.zeros_like(A) if need_dA else None), None
         dz = _req(dz, "dz")
         L = _lib.lib()
-        dA = torch.empty_like(A) if need_dA else None
+        direct_dA = need_dA and ctx.dA_target is not None
+        dA = (ctx.dA_target if direct_dA else torch.empty_like(A)) if need_dA else None
         dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
         n_ws = L.vcm_coeff_grad_workspace(t.handle, B, I, M) if need_dA else 0
         ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
@@ -92,7 +116,7 @@ class _GatherContract(torch.autograd.Function):
             dx = torch.empty_like(x)
             _lib.call("vcm_scatter_rev", t.handle, _ptr(dG), _ptr(dx), B, I, 0, st,
                       nbytes=gb + 4 * nnz + 4 * (p_in + 1) + 4 * x.numel(), flops=B * nnz * I, tag=tag)
-        return dx, (dA if need_dA else None), None
+        return dx, (dA if need_dA and not direct_dA else None), None
 
 
 class _BasisGemm(torch.autograd.Function):
@@ -132,6 +156,8 @@ class _BasisGemm(torch.autograd.Function):
         y_saved = (y_act if y_act is not None else out) if act else None
         ctx.save_for_backward(z, W, y_saved)
         ctx.cfg = (M, I, O, int(act), scale_y, scale_res, precision, per_point, bias is not None, res is not None)
+        ctx.dW_target = _grad_target(W) if W.requires_grad else None
+        ctx.db_target = _grad_target(bias) if bias is not None and bias.requires_grad else None
         return out
 
     @staticmethod
@@ -151,7 +177,10 @@ class _BasisGemm(torch.autograd.Function):
                     (torch.zeros(p_out, O, device=dev) if per_point else torch.zeros(O, device=dev)) if need_db else None,
                     torch.zeros_like(dout) if need_dres else None) + (None,) * 7
         ds = torch.empty_like(dout)
-        db_pp = torch.empty(p_out, O, device=dev, dtype=torch.float32) if need_db else None
+        direct_db = need_db and ctx.db_target is not None
+        db_pp = None
+        if need_db:
+            db_pp = ctx.db_target if (direct_db and per_point) else torch.empty(p_out, O, device=dev, dtype=torch.float32)
         dres = torch.empty_like(dout) if need_dres else None
         ny = dout.numel()
         tag = "R%d K%d O%d" % (B * p_out, K, O)
@@ -163,9 +192,11 @@ class _BasisGemm(torch.autograd.Function):
             if per_point:
                 dbias = db_pp
             else:
-                dbias = torch.empty(O, device=dev, dtype=torch.float32)
+                dbias = ctx.db_target if direct_db else torch.empty(O, device=dev, dtype=torch.float32)
                 _lib.call("vcm_colsum", _ptr(db_pp), _ptr(dbias), p_out, O, st, nbytes=4 * (p_out * O + O),
                           flops=p_out * O, tag=tag)
+            if direct_db:
+                dbias = None
         R = B * p_out
         dz = dW = None
         if need_dz:
@@ -175,11 +206,14 @@ class _BasisGemm(torch.autograd.Function):
             _lib.call("vcm_basis_bwd_dz", _ptr(ds), _ptr(W), _ptr(dz), _ptr(ws), R, M, I, O, 0, precision, st,
                       nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
         if need_dW:
-            dW = torch.empty_like(W)
+            direct_dW = ctx.dW_target is not None
+            dW = ctx.dW_target if direct_dW else torch.empty_like(W)
             n_ws = L.vcm_basis_bwd_dw_workspace(R, M, I, O, precision)
             ws = torch.empty(max(n_ws, 1), device=dev, dtype=torch.float32)
             _lib.call("vcm_basis_bwd_dw", _ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision, st,
                       nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
+            if direct_dW:
+                dW = None
         return (dz, dW, dbias, dres) + (None,) * 7
 
 
@@ -208,6 +242,7 @@ class _BiasAct(torch.autograd.Function):
                       tag="R%d O%d" % (B * p_out, O))
         ctx.save_for_backward((y_act if y_act is not None else out) if act else None)
         ctx.cfg = (int(act), scale_y, scale_res, per_point, bias is not None, res is not None, O)
+        ctx.db_target = _grad_target(bias) if bias is not None and bias.requires_grad else None
         return out
 
     @staticmethod
@@ -219,15 +254,21 @@ class _BiasAct(torch.autograd.Function):
         need_db = has_bias and ctx.needs_input_grad[1]
         need_dres = has_res and ctx.needs_input_grad[2]
         ds = torch.empty_like(dout)
-        db_pp = torch.empty(p_out, O, device=dout.device, dtype=torch.float32) if need_db else None
+        direct_db = need_db and ctx.db_target is not None
+        db_pp = None
+        if need_db:
+            db_pp = ctx.db_target if (direct_db and per_point) else torch.empty(p_out, O, device=dout.device,
+                                                                               dtype=torch.float32)
         dres = torch.empty_like(dout) if need_dres else None
         st = _lib.stream_ptr()
         _lib.call("vcm_act_bwd", _ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st,
                   nbytes=4 * dout.numel() * 3, flops=2 * dout.numel(), tag="R%d O%d" % (B * p_out, O))
         dbias = db_pp
         if need_db and not per_point:
-            dbias = torch.empty(O, device=dout.device, dtype=torch.float32)
+            dbias = ctx.db_target if direct_db else torch.empty(O, device=dout.device, dtype=torch.float32)
             _lib.call("vcm_colsum", _ptr(db_pp), _ptr(dbias), p_out, O, st, nbytes=4 * (p_out * O + O), flops=p_out * O)
+        if direct_db:
+            dbias = None
         return ds, dbias, dres, None, None, None
 
 
@@ -242,16 +283,18 @@ class _EdgeWeights(torch.autograd.Function):
                   nbytes=12 * p_nb.numel(), flops=3 * p_nb.numel())
         ctx.save_for_backward(p_nb)
         ctx.tables = tables
+        ctx.dp_target = _grad_target(p_nb) if p_nb.requires_grad else None
         return pn
 
     @staticmethod
     def backward(ctx, dpn):
         (p_nb,) = ctx.saved_tensors
         dpn = _req(dpn, "dpn")
-        dp = torch.empty_like(p_nb)
+        direct = ctx.dp_target is not None
+        dp = ctx.dp_target if direct else torch.empty_like(p_nb)
         _lib.call("vcm_edge_weights_bwd", ctx.tables.handle, _ptr(p_nb), _ptr(dpn), _ptr(dp), _lib.stream_ptr(),
                   nbytes=16 * p_nb.numel(), flops=6 * p_nb.numel())
-        return dp, None
+        return (None if direct else dp), None
 
 
 def gather_contract(x, coeffs, tables):

@@ -181,6 +181,7 @@ class DataParallelTrainer:
         self._handles = []
         if self.overlap:
             self._install_hooks()
+        self._set_direct_grads(not self.overlap)
         if self.world > 1:
             self.broadcast_parameters()
 
@@ -227,8 +228,15 @@ class DataParallelTrainer:
             dist.all_reduce(self.flat.flat_g, op=dist.ReduceOp.SUM, group=self.group)
 
     # -- one training step ---------------------------------------------------------
+    def _set_direct_grads(self, on):
+        """Backward kernels write parameter gradients straight into the flat buffer (no autograd
+        accumulate kernels). Needs no per-parameter hooks, so it is off while bucketed overlap is on."""
+        for p in self.flat.params:
+            p._vcm_grad_buf = p.grad if on else None
+
     def forward_backward(self, pc, nor, eps=None):
         self.flat.zero_grad()
+        F_.begin_step(self.flat.params)
         loss, l1, lap, kl, lnor, _ = self.model.losses(pc, nor, eps)
         loss.backward()
         return loss.detach(), (l1.detach(), lap.detach(), kl.detach(), lnor.detach())
@@ -267,6 +275,7 @@ class DataParallelTrainer:
         the two graphs on the same stream."""
         assert pc.is_cuda and self._graph is None
         self.overlap = False                         # no NCCL launches inside the capture
+        self._set_direct_grads(True)
         self.static_pc, self.static_nor = pc.clone(), nor.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
