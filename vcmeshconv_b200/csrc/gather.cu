@@ -128,32 +128,6 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx, const int32_t *__res
 }
 
 // ------------------------------------------------------------------ K5 ------
-// Butterfly transpose-reduce: every lane enters with vals[0..MT), lane l leaves
-// with the warp-wide sum of vals[l] in vals[0] (l < MT). 31 shuffles for
-// MT <= 32 instead of 5*MT.
-template <int MT>
-__device__ __forceinline__ float warp_transpose_reduce(float (&vals)[32], int lane) {
-    if (MT == 1) {                               // a single value: plain butterfly sum, every lane gets it
-        float v = vals[0];
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        return v;
-    }
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const bool upper = (lane & s) != 0;
-#pragma unroll
-        for (int j = 0; j < s; ++j) {
-            // values >= MT are structurally zero: the compiler drops their traffic
-            const float lo = vals[j], hi = vals[j + s];
-            const float send = upper ? lo : hi;
-            const float keep = upper ? hi : lo;
-            vals[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    return vals[0];
-}
-
 template <int MT, int VEC>
 __global__ void __launch_bounds__(kThreads, (MT > 17 ? 1 : 2))
 coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ last,
@@ -165,9 +139,13 @@ coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ l
     float *A_s = smem;                                                 // [TP][n_max][MP]
     float *part_s = A_s + (size_t)g.TP * n_max * MP;                   // [8 warps][n_max][MT]
     int32_t *idx_s = reinterpret_cast<int32_t *>(part_s + (size_t)8 * n_max * MT);   // [TP][n_max]
+    // per-warp scratch of the lane reduction: 2 buffers x [MT rows][36] floats (16-byte aligned rows)
+    constexpr int RS = 36;
+    float *red_s = reinterpret_cast<float *>(idx_s + ((size_t)g.TP * n_max + 3) / 4 * 4);
     __shared__ int32_t vert_s[8], last_s[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *red_w = red_s + (size_t)warp * 2 * MT * RS;
     if (tid < g.TP) {
         const int slot = blockIdx.x * g.TP + tid;
         const int p = slot < p_out ? perm[slot] : -1;
@@ -245,21 +223,39 @@ coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ l
             if (active && real && dG != nullptr) og.store(dGr + (size_t)n * I);
 
             if (dA_out != nullptr) {                     // kernel-uniform: constant coefficients need no dA
-            // dA: per-lane partial over the strip, then warp transpose-reduce
-                float vals[32];
+                // dA: per-lane partial over the strip, then a reduction over the 32 lanes of the warp.
+                if (MT == 1) {
+                    float v = 0.f;
 #pragma unroll
-                for (int m = 0; m < 32; ++m) {
-                    if (m < MT) {
-                        float s = 0.f;
+                    for (int j = 0; j < VEC; ++j) v = fmaf(d[0][j], gv.v[j], v);
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) s = fmaf(d[m][j], gv.v[j], s);
-                        vals[m] = s;
-                    } else {
-                        vals[m] = 0.f;
+                    for (int s2 = 16; s2 >= 1; s2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s2);
+                    if (lane == 0) pw[n] += v;
+                } else {
+                    // through shared memory: lane l stores its MT partials as column l of an [MT][36] tile
+                    // (conflict-free), then lane m sums row m with 8 LDS.128 (quarter-warps hit disjoint banks).
+                    // ~60 instructions per neighbour instead of ~125 for a shuffle butterfly; two buffers
+                    // alternate so one __syncwarp per neighbour is enough. Fixed order: bitwise reproducible.
+                    float *buf = red_w + (n & 1) * MT * RS;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        float sm = 0.f;
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) sm = fmaf(d[m][j], gv.v[j], sm);
+                        buf[m * RS + lane] = sm;
+                    }
+                    __syncwarp();
+                    if (lane < MT) {
+                        const float4 *row = reinterpret_cast<const float4 *>(buf + lane * RS);
+                        float tot = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 t4 = row[k];
+                            tot += (t4.x + t4.y) + (t4.z + t4.w);
+                        }
+                        pw[n * MT + lane] += tot;        // warp-private slot: no race
                     }
                 }
-                const float tot = warp_transpose_reduce<MT>(vals, lane);
-                if (lane < MT) pw[n * MT + lane] += tot; // warp-private slot: no race, fixed order
             }
         }
     }
@@ -413,7 +409,10 @@ template <int MT, int VEC>
 static int plan_grad(const Tables *t, int B, int I, GradPlan *pl) {
     constexpr int MP = round4(MT);
     ColumnGeom g = column_geom(B, I, VEC, 8);
-    auto bytes = [&](int tp) { return ((size_t)tp * t->n_max * (MP + 1) + (size_t)8 * t->n_max * MT) * sizeof(float); };
+    auto bytes = [&](int tp) {
+        return ((size_t)tp * t->n_max * MP + (size_t)8 * t->n_max * MT + ((size_t)tp * t->n_max + 3) / 4 * 4 +
+                (size_t)8 * 2 * MT * 36) * sizeof(float);
+    };
     while (g.TP > 1 && bytes(g.TP) > (size_t)kMaxSmem) { g.TP /= 2; g.CB *= 2; }
     if (bytes(g.TP) > (size_t)kMaxSmem)
         return fail(VCM_EUNSUPPORTED, "neighbour count %d too large for the staging buffer", t->n_max);

@@ -33,7 +33,6 @@ namespace {
 
 constexpr int TM = 128;           // accumulator rows per CTA (UMMA M)
 constexpr int TK = 32;            // fp32 per k-block: one 128-byte swizzle row
-constexpr int STAGES = 4;
 constexpr int A_BYTES = TM * TK * 4;          // 16 KB
 constexpr int NTHREADS = 256;
 
@@ -171,7 +170,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn, int a_mn_major, int b_
 __device__ __forceinline__ float elu1(float t) { return t > 0.f ? t : expm1f(t); }
 
 // --------------------------------------------------------------------- kernel --
-template <int BN, int MODE>
+// STAGES: depth of the TMA -> MMA ring. Long reductions (K2, K4) use 4 stages and own the SM; the dz GEMM
+// has a short reduction (O/32 <= 16 k-blocks) and a large output tile, so it runs with 2 stages and two CTAs
+// per SM: one CTA's epilogue stores overlap the other's loads and MMAs.
+template <int BN, int MODE, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
     constexpr int B_BYTES = BN * TK * 4;
@@ -434,11 +436,11 @@ int pick_bn(int n) {       // n % 32 == 0
     return 32;
 }
 
-template <int MODE>
+template <int MODE, int STAGES>
 int launch(int bn, dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, cudaStream_t st) {
 #define VCM_TC_CASE(BN_)                                                                                          \
     case BN_: {                                                                                                   \
-        auto k = tc_gemm_kernel<BN_, MODE>;                                                                       \
+        auto k = tc_gemm_kernel<BN_, MODE, STAGES>;                                                               \
         const int smem = STAGES * (A_BYTES + BN_ * TK * 4) + 1024 + 256;                                          \
         VCM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
         k<<<grid, NTHREADS, smem, st>>>(ma, mb, p);                                                               \
@@ -526,7 +528,7 @@ int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_poin
     p.bias = bias; p.res = res; p.y_act = y_act; p.out = out; p.per_point = per_point; p.act = act; p.sy = sy; p.sr = sr;
     p.partial = n_split > 1 ? ws : nullptr;
     dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(O, bn), (unsigned)n_split);
-    if (int e = launch<MODE_FWD>(bn, grid, ma, mb, p, st)) return e;
+    if (int e = launch<MODE_FWD, 4>(bn, grid, ma, mb, p, st)) return e;
     if (n_split > 1) {
         splitk_fwd_epilogue_kernel<<<(unsigned)ceil_div(R * O / 4, 256), 256, 0, st>>>(ws, n_split, R, O, P_out, bias,
                                                                                       per_point, res, y_act, out, act,
@@ -563,7 +565,7 @@ int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64
     p.num_kb = O / TK; p.kb_per_m = p.num_kb; p.kb_per_split = p.num_kb;
     p.out = dz;
     dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(K, bn), 1);
-    return launch<MODE_DZ>(bn, grid, ma, mb, p, st);
+    return launch<MODE_DZ, 2>(bn, grid, ma, mb, p, st);
 }
 
 size_t tc_basis_bwd_dw_workspace(int64_t R, int M, int I, int O, int precision) {
@@ -594,7 +596,7 @@ int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64
     p.direct = sp.n_split == 1;
     p.out = p.direct ? dW : ws;
     dim3 grid((unsigned)ceil_div(K, TM), (unsigned)ceil_div(O, bn), (unsigned)sp.n_split);
-    if (int e = launch<MODE_DW>(bn, grid, ma, mb, p, st)) return e;
+    if (int e = launch<MODE_DW, 4>(bn, grid, ma, mb, p, st)) return e;
     if (p.direct) return VCM_OK;
     const size_t n = (size_t)K * O;
     sum_partials_kernel<<<(unsigned)ceil_div((int64_t)(n / 4), 256), 256, 0, st>>>(ws, dW, n, sp.n_split);
