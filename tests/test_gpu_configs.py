@@ -1,0 +1,126 @@
+"""The other BASELINE configs as parity cases (bench.py measures C2 only):
+  C3  FLAME-sized 5023-vertex autoencoder, batch 64
+  C4  ~150k-vertex template, batch 8 (single layers at full size)
+  C5  tetrahedral / non-manifold template with irregular degree, N_max around 32
+At these sizes the fp64 oracle is run where it finishes in seconds; elsewhere
+size-independent properties are checked (linearity, batch independence,
+determinism, exact zeros on padding)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import vcconv_oracle as orc
+from vcmeshconv_b200 import graph_sampling as gs
+from vcmeshconv_b200 import graphVAE_train as T
+from vcmeshconv_b200 import graphVAESSW as vae
+from vcmeshconv_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _oracle_vs_cuda(table, p_in, cin, cout, m, batch, resid, seed, tol=TOL):
+    gen = torch.Generator().manual_seed(seed)
+    layer_o = orc.Layer(table, cin, cout, p_in, resid)
+    params = orc.init_layer_params(table, cin, cout, m, p_in, True, resid, gen, torch.float64)
+    params["bias"] = torch.randn(params["bias"].shape, generator=gen, dtype=torch.float64) * 0.1
+    coeffs = orc.init_coeffs(table, m, gen, torch.float64) * 4
+    x = torch.randn(batch, p_in, cin, generator=gen, dtype=torch.float64) * 0.3
+    gy = torch.randn(batch, table.shape[0], cout, generator=gen, dtype=torch.float64)
+    for t in [x, coeffs] + list(params.values()):
+        t.requires_grad_(True)
+    y_ref = layer_o(x, coeffs, params)
+    y_ref.backward(gy)
+    layer = vae.LASMConvssw(cin, cout, m, p_in, table, True, resid)
+    layer.load_state_dict({**{k: v.detach().float() for k, v in params.items()},
+                           "neighbor_num_lst": layer.neighbor_num_lst, "neighbor_id_lstlst": layer.neighbor_id_lstlst})
+    layer = layer.cuda()
+    xg = x.detach().float().cuda().requires_grad_(True)
+    Ag = coeffs.detach().float().cuda().requires_grad_(True)
+    y = layer(xg, Ag)
+    y.backward(gy.float().cuda())
+    assert rel_err(y.detach().cpu().numpy(), y_ref.detach().numpy()) < tol
+    assert rel_err(xg.grad.cpu().numpy(), x.grad.numpy()) < tol
+    assert rel_err(Ag.grad.cpu().numpy(), coeffs.grad.numpy()) < tol
+    for k, p in layer.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), params[k].grad.numpy()) < tol, k
+    pad = layer.neighbor_id_lstlst.cpu().numpy() == p_in
+    assert np.all(Ag.grad.cpu().numpy()[pad] == 0)
+
+
+@pytest.fixture(scope="module")
+def sphere150k():
+    pts, faces = synthetic.sphere(150000, seed=0)
+    tabs, nums = gs.build_tables(faces, 150000, [(1, 1, 1), (2, 2, 2)])
+    return tabs, nums
+
+
+def test_c4_pool_layer_vs_oracle(sphere150k):
+    tabs, nums = sphere150k                      # pool1: 150000 -> ~39.8k vertices, N ~ 40
+    assert nums[0] == 150000 and tabs["pool1"].shape[0] == nums[2]
+    _oracle_vs_cuda(tabs["pool1"], 150000, 3, 32, 17, 1, 0.9, 41)
+
+
+def test_c4_unpool_layer_vs_oracle(sphere150k):
+    tabs, nums = sphere150k                      # unpool1: ~39.8k -> 150000 vertices, 32 -> 3 (project-first order)
+    _oracle_vs_cuda(tabs["unpool1"], nums[2], 32, 3, 17, 1, 0.9, 42)
+
+
+def test_c4_full_size_batch8_properties(sphere150k):
+    tabs, nums = sphere150k
+    torch.manual_seed(0)
+    layer = vae.LASMConvssw(32, 32, 17, 150000, tabs["pool0"], True, 0.0).cuda()      # conv at full resolution
+    A = (torch.randn(150000, layer.max_neighbor_num, 17) / (7 * 17)).cuda()
+    x1 = (torch.randn(8, 150000, 32) * 0.3).cuda()
+    x2 = (torch.randn(8, 150000, 32) * 0.3).cuda()
+    with torch.no_grad():
+        f = lambda x: layer(x, A, is_final_layer=True)
+        y1, y2 = f(x1), f(x2)
+        assert rel_err(f(0.5 * x1 + 2.0 * x2).cpu().numpy(), (0.5 * y1 + 2.0 * y2).cpu().numpy()) < TOL
+        assert torch.equal(f(x1[5:6]), y1[5:6])
+    xa = x1.clone().requires_grad_(True)
+    Aa = A.clone().requires_grad_(True)
+    layer(xa, Aa).square().mean().backward()
+    g1 = (xa.grad.clone(), Aa.grad.clone(), layer.weights.grad.clone())
+    xa.grad = Aa.grad = None
+    layer.zero_grad()
+    layer(xa, Aa).square().mean().backward()
+    for a, b in zip(g1, (xa.grad, Aa.grad, layer.weights.grad)):
+        assert torch.equal(a, b)                                                   # bitwise deterministic
+
+
+def test_c5_tetrahedral_irregular_degree():
+    pts, faces = synthetic.tets(3000, seed=3)
+    tabs, nums = gs.build_tables(faces, 3000, [(1, 1, 1), (2, 2, 2)])
+    n0 = (tabs["pool0"].shape[1] - 1) // 2
+    cnt = tabs["pool0"][:, 0]
+    assert 24 <= n0 <= 48 and cnt.min() < n0 // 2          # long degree tail: heavy padding
+    _oracle_vs_cuda(tabs["pool0"], 3000, 16, 32, 17, 2, 0.0, 51)
+    _oracle_vs_cuda(tabs["pool1"], 3000, 32, 64, 17, 2, 0.9, 52)        # pooling balls with N > 100
+    _oracle_vs_cuda(tabs["unpool1"], nums[2], 64, 32, 17, 2, 0.9, 53)
+
+
+def test_c3_flame_sized_autoencoder_trains_batch64():
+    pts, faces = synthetic.sphere(5023, seed=0)
+    assert faces.shape[0] == 10042
+    tabs, nums = gs.build_tables(faces, 5023, synthetic.alternating_levels(7))
+    enc = [tabs["pool%d" % l] for l in range(1, 7)]
+    dec = [tabs["unpool%d" % l] for l in range(6, 0, -1)]
+    torch.manual_seed(0)
+    model = T.Net_autoenc(T.make_param(enc, dec, tabs["pool0"], 5023, 0.9), faces).cuda()
+    pc = torch.from_numpy(pts)[None].repeat(64, 1, 1).cuda() * 0.9 + torch.randn(64, 5023, 3, device="cuda") * 0.02
+    nor = torch.from_numpy(synthetic.face_normals(pc.cpu().numpy(), faces)).float().cuda()
+    eps = torch.randn(64, model.nrpt_latent, 64, device="cuda")
+    # batch independence of the whole network (bit-exact): a mesh's reconstruction does not depend on its batch
+    with torch.no_grad():
+        full = model.losses(pc, nor, eps)[5]
+        part = model.losses(pc[10:14], nor[10:14], eps[10:14])[5]
+    assert torch.equal(full[10:14], part)
+    tr = T.DataParallelTrainer(model, lr=1e-4)
+    first = last = None
+    for it in range(8):
+        loss, _ = tr.step(pc, nor, eps)
+        first = loss.item() if first is None else first
+        last = loss.item()
+    assert np.isfinite(last) and last < first
