@@ -74,6 +74,9 @@ VCM_API int vcm_basis_uses_tensor_cores(int64_t rows, int M, int I, int O, int p
  *   last     int32 [P_out]      1 + position of the last non-sentinel entry
  *   perm     int32 [P_out]      output vertices sorted by `last` descending
  *                               (stable) = degree-bucketed processing order
+ *   idx_sorted  int32 [P_out, N]  rows of idx in `perm` order, meta_sorted int32 [P_out, 2] = {vertex,
+ *                               last} in `perm` order: what a CTA needs for work item s sits at
+ *                               addresses that depend on s only
  *   rev_ptr  int32 [P_in + 1]   CSR row pointers of the transposed graph
  *   rev_slot int32 [nnz]        for input vertex q the slots p*N+n with
  *                               idx[p,n] == q, ascending (deterministic dX)
@@ -88,7 +91,8 @@ typedef struct vcm_tables_info {
     int32_t device;
 } vcm_tables_info;
 
-enum { VCM_TAB_IDX = 0, VCM_TAB_LAST = 1, VCM_TAB_PERM = 2, VCM_TAB_REV_PTR = 3, VCM_TAB_REV_SLOT = 4 };
+enum { VCM_TAB_IDX = 0, VCM_TAB_LAST = 1, VCM_TAB_PERM = 2, VCM_TAB_REV_PTR = 3, VCM_TAB_REV_SLOT = 4,
+       VCM_TAB_IDX_SORTED = 5, VCM_TAB_META_SORTED = 6 };
 
 VCM_API int vcm_tables_create(const int32_t *table_host, int p_out, int cols, int p_in, vcm_tables **out);
 VCM_API void vcm_tables_destroy(vcm_tables *t);

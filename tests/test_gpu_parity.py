@@ -47,6 +47,8 @@ def test_device_tables_bit_exact(case):
     assert np.array_equal(t.export(_lib.TAB_PERM), want["perm"])
     assert np.array_equal(t.export(_lib.TAB_REV_PTR), want["rev_ptr"])
     assert np.array_equal(t.export(_lib.TAB_REV_SLOT), want["rev_slot"])
+    assert np.array_equal(t.export(_lib.TAB_IDX_SORTED).reshape(want["idx"].shape), want["idx_sorted"])
+    assert np.array_equal(t.export(_lib.TAB_META_SORTED).reshape(-1, 2), want["meta_sorted"])
     assert t.nnz == int((g["param.neighbor_id_lstlst"] != p_in).sum())
 
 

@@ -13,7 +13,7 @@ _lib = None
 
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
-TAB_IDX, TAB_LAST, TAB_PERM, TAB_REV_PTR, TAB_REV_SLOT = range(5)
+TAB_IDX, TAB_LAST, TAB_PERM, TAB_REV_PTR, TAB_REV_SLOT, TAB_IDX_SORTED, TAB_META_SORTED = range(7)
 
 _p, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 

@@ -58,7 +58,8 @@ class DeviceTables:
 
     def export(self, which):
         sizes = {_lib.TAB_IDX: self.p_out * self.n_max, _lib.TAB_LAST: self.p_out, _lib.TAB_PERM: self.p_out,
-                 _lib.TAB_REV_PTR: self.p_in + 1, _lib.TAB_REV_SLOT: self.nnz}
+                 _lib.TAB_REV_PTR: self.p_in + 1, _lib.TAB_REV_SLOT: self.nnz,
+                 _lib.TAB_IDX_SORTED: self.p_out * self.n_max, _lib.TAB_META_SORTED: 2 * self.p_out}
         out = np.empty(sizes[which], dtype=np.int32)
         _lib.check(_lib.lib().vcm_tables_export(self._h, which, out.ctypes.data, out.size))
         return out
@@ -90,4 +91,5 @@ def derive_host(table, in_point_num):
     rev_ptr = np.zeros(in_point_num + 1, np.int32)
     np.add.at(rev_ptr, q + 1, 1)
     rev_ptr = np.cumsum(rev_ptr).astype(np.int32)
-    return {"idx": ids.astype(np.int32), "last": last, "perm": perm, "rev_ptr": rev_ptr, "rev_slot": rev_slot}
+    return {"idx": ids.astype(np.int32), "last": last, "perm": perm, "rev_ptr": rev_ptr, "rev_slot": rev_slot,
+            "idx_sorted": ids.astype(np.int32)[perm], "meta_sorted": np.stack([perm, last[perm]], 1).astype(np.int32)}

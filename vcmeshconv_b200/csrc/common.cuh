@@ -59,6 +59,8 @@ struct Tables {
     int32_t *perm = nullptr;      // [p_out]
     int32_t *rev_ptr = nullptr;   // [p_in + 1]
     int32_t *rev_slot = nullptr;  // [nnz]
+    int32_t *idx_sorted = nullptr;   // [p_out, n_max] rows of idx in `perm` order
+    int32_t *meta_sorted = nullptr;  // [p_out, 2] {vertex, last} in `perm` order (one 8-byte load per work item)
     int32_t *blob = nullptr;      // single allocation backing all of the above
 };
 

@@ -31,59 +31,58 @@ struct ColumnGeom {
     int IV;     // I / VEC
 };
 
-static ColumnGeom column_geom(int B, int I, int vec, int max_tp) {
+static ColumnGeom column_geom(int B, int I, int vec, int max_tp, int threads = kThreads) {
     ColumnGeom g;
     g.IV = I / vec;
     g.C = B * g.IV;
     int tp = 1;
-    while (tp < max_tp && kThreads / (tp * 2) >= g.C) tp *= 2;   // shrink CB while it still covers C
+    while (tp < max_tp && threads / (tp * 2) >= g.C && threads / (tp * 2) >= 32) tp *= 2;   // CB stays a warp multiple
     g.TP = tp;
-    g.CB = kThreads / tp;
+    g.CB = threads / tp;
     return g;
 }
 
 // ------------------------------------------------------------------ K1 ------
+// K1 runs 128-thread CTAs, four per SM: the staging round trip of one CTA (a full L2 latency before its
+// barrier) then idles a quarter of the SM's warps instead of half.
+constexpr int kFwdThreads = 128;
 template <int MT, int VEC>
-__global__ void __launch_bounds__(kThreads, (MT > 17 ? 1 : 2))
-gather_contract_fwd_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ last,
-                           const int32_t *__restrict__ perm, const float *__restrict__ x,
-                           const float *__restrict__ A, float *__restrict__ z, int p_in, int p_out, int n_max,
-                           int I, int M, ColumnGeom g) {
+__global__ void __launch_bounds__(kFwdThreads, (MT > 17 ? 2 : 4))
+gather_contract_fwd_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
+                           const float *__restrict__ x, const float *__restrict__ A, float *__restrict__ z, int p_in,
+                           int p_out, int n_max, int I, int M, ColumnGeom g) {
     constexpr int MP = round4(MT);
     extern __shared__ __align__(16) float smem[];
     float *A_s = smem;                                               // [TP][n_max][MP]
     int32_t *idx_s = reinterpret_cast<int32_t *>(smem + (size_t)g.TP * n_max * MP);  // [TP][n_max]
-    __shared__ int32_t vert_s[8], last_s[8];
 
+    // Work item s = blockIdx.x*TP + v: {vertex, trip count} and the neighbour ids sit at addresses that depend
+    // on s only (processing-order tables), so the staging below is ONE round of independent loads + one barrier.
     const int tid = threadIdx.x;
-    if (tid < g.TP) {
-        const int slot = blockIdx.x * g.TP + tid;
-        const int p = slot < p_out ? perm[slot] : -1;
-        vert_s[tid] = p;
-        last_s[tid] = p >= 0 ? last[p] : 0;
-    }
-    __syncthreads();
     for (int v = 0; v < g.TP; ++v) {
-        const int p = vert_s[v], l = last_s[v];
-        if (p < 0) continue;
+        const int slot = blockIdx.x * g.TP + v;
+        if (slot >= p_out) break;
+        const int2 meta = __ldg(meta_sorted + slot);                 // block-uniform broadcast
+        const int p = meta.x, l = meta.y;
         const float *Ap = A + (size_t)p * n_max * M;
-        for (int e = tid; e < l * MP; e += kThreads) {
+        for (int e = tid; e < l * MP; e += kFwdThreads) {
             const int n = e / MP, m = e - n * MP;
             A_s[((size_t)v * n_max + n) * MP + m] = m < M ? __ldg(Ap + n * M + m) : 0.f;
         }
-        for (int n = tid; n < l; n += kThreads) idx_s[v * n_max + n] = __ldg(idx + (size_t)p * n_max + n);
+        for (int n = tid; n < l; n += kFwdThreads) idx_s[v * n_max + n] = __ldg(idx_sorted + (size_t)slot * n_max + n);
     }
     __syncthreads();
 
     const int v = tid / g.CB;
     const int c = blockIdx.y * g.CB + (tid - v * g.CB);
-    const int p = vert_s[v];
-    if (p < 0 || c >= g.C) return;
+    const int slot = blockIdx.x * g.TP + v;
+    if (slot >= p_out || c >= g.C) return;
+    const int2 meta = __ldg(meta_sorted + slot);
+    const int p = meta.x, l = meta.y;
     const int b = c / g.IV, i0 = (c - b * g.IV) * VEC;
     const float *xb = x + (size_t)b * p_in * I + i0;
     const float *Av = A_s + (size_t)v * n_max * MP;
     const int32_t *iv = idx_s + v * n_max;
-    const int l = last_s[v];
 
     float acc[MT][VEC];
 #pragma unroll
@@ -130,10 +129,10 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx, const int32_t *__res
 // ------------------------------------------------------------------ K5 ------
 template <int MT, int VEC>
 __global__ void __launch_bounds__(kThreads, (MT > 17 ? 1 : 2))
-coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ last,
-                  const int32_t *__restrict__ perm, const float *__restrict__ dz, const float *__restrict__ x,
-                  const float *__restrict__ A, float *__restrict__ dA_out, float *__restrict__ dG, int p_in,
-                  int p_out, int n_max, int I, int M, ColumnGeom g, int passes_per_split, int n_split) {
+coeff_grad_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
+                  const float *__restrict__ dz, const float *__restrict__ x, const float *__restrict__ A,
+                  float *__restrict__ dA_out, float *__restrict__ dG, int p_in, int p_out, int n_max, int I, int M,
+                  ColumnGeom g, int passes_per_split, int n_split) {
     constexpr int MP = round4(MT);
     extern __shared__ __align__(16) float smem[];
     float *A_s = smem;                                                 // [TP][n_max][MP]
@@ -146,23 +145,26 @@ coeff_grad_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ l
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *red_w = red_s + (size_t)warp * 2 * MT * RS;
-    if (tid < g.TP) {
-        const int slot = blockIdx.x * g.TP + tid;
-        const int p = slot < p_out ? perm[slot] : -1;
-        vert_s[tid] = p;
-        last_s[tid] = p >= 0 ? last[p] : 0;
-    }
     for (int e = tid; e < 8 * n_max * MT; e += kThreads) part_s[e] = 0.f;
-    __syncthreads();
     for (int v = 0; v < g.TP; ++v) {
-        const int p = vert_s[v], l = last_s[v];
+        const int slot = blockIdx.x * g.TP + v;
+        int p = -1, l = 0;
+        if (slot < p_out) {
+            const int2 meta = __ldg(meta_sorted + slot);               // block-uniform broadcast
+            p = meta.x;
+            l = meta.y;
+        }
+        if (tid == 0) {
+            vert_s[v] = p;
+            last_s[v] = l;
+        }
         if (p < 0) continue;
         const float *Ap = A + (size_t)p * n_max * M;
         for (int e = tid; e < l * MP; e += kThreads) {
             const int n = e / MP, m = e - n * MP;
             A_s[((size_t)v * n_max + n) * MP + m] = m < M ? __ldg(Ap + n * M + m) : 0.f;
         }
-        for (int n = tid; n < l; n += kThreads) idx_s[v * n_max + n] = __ldg(idx + (size_t)p * n_max + n);
+        for (int n = tid; n < l; n += kThreads) idx_s[v * n_max + n] = __ldg(idx_sorted + (size_t)slot * n_max + n);
     }
     __syncthreads();
 
@@ -386,7 +388,7 @@ template <int MT, int VEC>
 static int launch_fwd(const Tables *t, const float *x, const float *A, float *z, int B, int I, int M,
                       cudaStream_t st) {
     constexpr int MP = round4(MT);
-    ColumnGeom g = column_geom(B, I, VEC, 8);
+    ColumnGeom g = column_geom(B, I, VEC, 4, kFwdThreads);
     auto bytes = [&](int tp) { return (size_t)tp * t->n_max * (MP + 1) * sizeof(float); };
     while (g.TP > 1 && bytes(g.TP) > (size_t)kMaxSmem) { g.TP /= 2; g.CB *= 2; }
     if (bytes(g.TP) > (size_t)kMaxSmem)
@@ -394,7 +396,8 @@ static int launch_fwd(const Tables *t, const float *x, const float *A, float *z,
     auto k = gather_contract_fwd_kernel<MT, VEC>;
     if (int e = set_smem(k, bytes(g.TP))) return e;
     dim3 grid((unsigned)ceil_div(t->p_out, g.TP), (unsigned)ceil_div(g.C, g.CB));
-    k<<<grid, kThreads, bytes(g.TP), st>>>(t->idx, t->last, t->perm, x, A, z, t->p_in, t->p_out, t->n_max, I, M, g);
+    k<<<grid, kFwdThreads, bytes(g.TP), st>>>(t->idx_sorted, reinterpret_cast<const int2 *>(t->meta_sorted), x, A, z, t->p_in,
+                                            t->p_out, t->n_max, I, M, g);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
@@ -439,7 +442,8 @@ static int launch_grad(const Tables *t, const float *dz, const float *x, const f
         return fail(VCM_EINVAL, "workspace required (%d splits)", pl.n_split);
     float *target = dA == nullptr ? nullptr : (pl.n_split > 1 ? ws : dA);
     dim3 grid((unsigned)ceil_div(t->p_out, pl.g.TP), (unsigned)pl.n_split);
-    k<<<grid, kThreads, pl.smem, st>>>(t->idx, t->last, t->perm, dz, x, A, target, dG, t->p_in, t->p_out, t->n_max,
+    k<<<grid, kThreads, pl.smem, st>>>(t->idx_sorted, reinterpret_cast<const int2 *>(t->meta_sorted), dz, x, A, target, dG,
+                                       t->p_in, t->p_out, t->n_max,
                                        I, M, pl.g, pl.passes, pl.n_split);
     VCM_LAUNCH_CHECK();
     if (dA != nullptr && pl.n_split > 1) {

@@ -117,6 +117,17 @@ int vcm_tables_create(const int32_t *table, int p_out, int cols, int p_in, vcm_t
             }
     }
 
+    // processing-order copies: a CTA finds vertex id, trip count and neighbour ids of its work item at
+    // addresses that depend on the slot only (no perm -> last -> idx chain of dependent loads)
+    std::vector<int32_t> idx_sorted(idx.size()), meta_sorted((size_t)p_out * 2);
+    for (int s2 = 0; s2 < p_out; ++s2) {
+        const int p = perm[s2];
+        meta_sorted[2 * (size_t)s2] = p;
+        meta_sorted[2 * (size_t)s2 + 1] = last[p];
+        std::copy(idx.begin() + (size_t)p * n_max, idx.begin() + (size_t)(p + 1) * n_max,
+                  idx_sorted.begin() + (size_t)s2 * n_max);
+    }
+
     Tables *t = new (std::nothrow) Tables;
     if (!t) return vcm::fail(VCM_ENOMEM, "out of host memory");
     t->p_in = p_in;
@@ -131,7 +142,8 @@ int vcm_tables_create(const int32_t *table, int p_out, int cols, int p_in, vcm_t
     auto pad = [](size_t n) { return (n + 63) / 64 * 64; };
     const size_t o_idx = 0, o_last = o_idx + pad(idx.size()), o_perm = o_last + pad(last.size()),
                  o_ptr = o_perm + pad(perm.size()), o_slot = o_ptr + pad(rev_ptr.size()),
-                 total = o_slot + pad(rev_slot.size()) + 64;
+                 o_is = o_slot + pad(rev_slot.size()), o_ms = o_is + pad(idx_sorted.size()),
+                 total = o_ms + pad(meta_sorted.size()) + 64;
     cudaError_t e = cudaMalloc(&t->blob, total * sizeof(int32_t));
     if (e != cudaSuccess) {
         delete t;
@@ -142,13 +154,16 @@ int vcm_tables_create(const int32_t *table, int p_out, int cols, int p_in, vcm_t
     t->perm = t->blob + o_perm;
     t->rev_ptr = t->blob + o_ptr;
     t->rev_slot = t->blob + o_slot;
+    t->idx_sorted = t->blob + o_is;
+    t->meta_sorted = t->blob + o_ms;
     auto up = [&](int32_t *dst, const std::vector<int32_t> &src) {
         return src.empty() ? cudaSuccess
                            : cudaMemcpy(dst, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
     };
     if ((e = up(t->idx, idx)) != cudaSuccess || (e = up(t->last, last)) != cudaSuccess ||
         (e = up(t->perm, perm)) != cudaSuccess || (e = up(t->rev_ptr, rev_ptr)) != cudaSuccess ||
-        (e = up(t->rev_slot, rev_slot)) != cudaSuccess) {
+        (e = up(t->rev_slot, rev_slot)) != cudaSuccess || (e = up(t->idx_sorted, idx_sorted)) != cudaSuccess ||
+        (e = up(t->meta_sorted, meta_sorted)) != cudaSuccess) {
         cudaFree(t->blob);
         delete t;
         return vcm::fail((int)e, "table upload failed: %s", cudaGetErrorString(e));
@@ -184,6 +199,8 @@ static const int32_t *pick(const Tables *t, int which, size_t *n) {
         case VCM_TAB_PERM: *n = t->p_out; return t->perm;
         case VCM_TAB_REV_PTR: *n = (size_t)t->p_in + 1; return t->rev_ptr;
         case VCM_TAB_REV_SLOT: *n = (size_t)t->nnz; return t->rev_slot;
+        case VCM_TAB_IDX_SORTED: *n = (size_t)t->p_out * t->n_max; return t->idx_sorted;
+        case VCM_TAB_META_SORTED: *n = (size_t)t->p_out * 2; return t->meta_sorted;
     }
     *n = 0;
     return nullptr;
