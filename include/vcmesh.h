@@ -110,6 +110,17 @@ VCM_API const int32_t *vcm_tables_device_ptr(const vcm_tables *t, int which);
 VCM_API int vcm_gather_contract_fwd(const vcm_tables *t, const float *x, const float *A, float *z,
                                     int B, int I, int M, void *stream);
 
+/* Project-first order for narrow outputs (M*O <= 64; the 32 -> 3 layer on the full mesh). With
+ * u[b,q,m,o] = sum_i W[m,o,i] x[b,q,i] computed by vcm_basis_fwd (bases stacked along the output axis):
+ *   fwd: s[b,p,o]    = sum_{n,m} A[p,n,m] u[b, idx[p,n], m, o]
+ *   bwd: dA[p,n,m]   = sum_{b,o} ds[b,p,o] u[b, idx[p,n], m, o]      (0 on padding; NULL to skip)
+ *        du[b,q,m,o] = sum_{(p,n): idx[p,n]=q} A[p,n,m] ds[b,p,o]    (reverse CSR; NULL to skip)
+ * Same result as graphVAESSW.py:121-133 (the op is bilinear), without materialising z. */
+VCM_API int vcm_project_gather_fwd(const vcm_tables *t, const float *u, const float *A, float *s, int B, int M,
+                                   int O, void *stream);
+VCM_API int vcm_project_gather_bwd(const vcm_tables *t, const float *ds, const float *u, const float *A, float *dA,
+                                   float *du, int B, int M, int O, void *stream);
+
 /* Backward of the above w.r.t. A and the gathered rows (K5):
  *   dA[p,n,m]   = sum_{b,i} dz[b,p,m,i] * x[b, idx[p,n], i]     (0 on padding)
  *   dG[b,p,n,i] = sum_m A[p,n,m] * dz[b,p,m,i]                  (real edges only)

@@ -567,3 +567,199 @@ int vcm_edge_weights_bwd(const vcm_tables *h, const float *p_nb, const float *dp
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Project-first order for narrow outputs (last decoder layer, 32 -> 3 channels on the full mesh):
+//   u[b,q,m,o] = sum_i W[m,o,i] x[b,q,i]                       (one small GEMM, done by the caller)
+//   s[b,p,o]   = sum_{n,m} A[p,n,m] u[b, idx[p,n], m, o]        (vcm_project_gather_fwd)
+//   dA[p,n,m]  = sum_{b,o} ds[b,p,o] u[b, idx[p,n], m, o]       (vcm_project_gather_bwd)
+//   du[b,q,m,o]= sum_{(p,n) in rev(q)} A[p,n,m] ds[b,p,o]       (vcm_project_gather_bwd)
+// The op is bilinear, so this equals the gather-first result; it moves rows of M*O floats (51 for O = 3)
+// instead of materialising z (M*I = 544 floats per output vertex). One warp owns one (vertex, batch group);
+// lane j owns element j = m*O + o of the projected row (MO <= 64: two elements per lane), so every load of
+// a u row is one coalesced 4*MO-byte segment. Fixed-order reductions, no atomics.
+namespace vcm {
+
+constexpr int PG_MAXN = 16;       // neighbours handled per register pass of the dA kernel
+
+template <int NB>                 // NB = batch entries per warp pass
+__global__ void __launch_bounds__(128)
+project_gather_fwd_kernel(const int32_t *__restrict__ idx, const float *__restrict__ u, const float *__restrict__ A,
+                          float *__restrict__ s, int p_in, int p_out, int n_max, int B, int M, int O) {
+    __shared__ float red[4][NB][64];
+    const int MO = M * O, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int p = blockIdx.x * 4 + w;
+    if (p >= p_out) return;
+    const int j0 = lane, j1 = lane + 32;
+    const int m0 = j0 / O, m1 = j1 / O;
+    const bool v0 = j0 < MO, v1 = j1 < MO;
+    const int32_t *ip = idx + (size_t)p * n_max;
+    const float *Ap = A + (size_t)p * n_max * M;
+    for (int b0 = blockIdx.y * NB; b0 < B; b0 += gridDim.y * NB) {
+        float a0[NB], a1[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) a0[k] = a1[k] = 0.f;
+        for (int n = 0; n < n_max; ++n) {
+            const int q = __ldg(ip + n);
+            if (q == p_in) continue;                                   // warp-uniform
+            const float c0 = v0 ? __ldg(Ap + n * M + m0) : 0.f, c1 = v1 ? __ldg(Ap + n * M + m1) : 0.f;
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                if (b0 + k < B) {
+                    const float *ur = u + ((size_t)(b0 + k) * p_in + q) * MO;
+                    if (v0) a0[k] = fmaf(c0, __ldg(ur + j0), a0[k]);
+                    if (v1) a1[k] = fmaf(c1, __ldg(ur + j1), a1[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            red[w][k][j0] = a0[k];
+            red[w][k][j1] = a1[k];
+        }
+        __syncwarp();
+        // lane (k, o) sums its M products in fixed order
+        for (int e = lane; e < NB * O; e += 32) {
+            const int k = e / O, o = e - k * O;
+            if (b0 + k < B) {
+                float t = 0.f;
+                for (int m = 0; m < M; ++m) t += red[w][k][m * O + o];
+                s[((size_t)(b0 + k) * p_out + p) * O + o] = t;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// dA: one warp per output vertex, all batch entries, neighbours in register passes of PG_MAXN.
+__global__ void __launch_bounds__(128)
+project_gather_dA_kernel(const int32_t *__restrict__ idx, const float *__restrict__ ds, const float *__restrict__ u,
+                         float *__restrict__ dA, int p_in, int p_out, int n_max, int B, int M, int O) {
+    __shared__ float red[4][64];
+    const int MO = M * O, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int p = blockIdx.x * 4 + w;
+    if (p >= p_out) return;
+    const int j0 = lane, j1 = lane + 32;
+    const bool v0 = j0 < MO, v1 = j1 < MO;
+    const int o0 = j0 % O, o1 = j1 % O;
+    const int32_t *ip = idx + (size_t)p * n_max;
+    float *dAp = dA + (size_t)p * n_max * M;
+    for (int nb = 0; nb < n_max; nb += PG_MAXN) {
+        float a0[PG_MAXN], a1[PG_MAXN];
+        int q[PG_MAXN];
+#pragma unroll
+        for (int k = 0; k < PG_MAXN; ++k) {
+            a0[k] = a1[k] = 0.f;
+            q[k] = nb + k < n_max ? __ldg(ip + nb + k) : p_in;
+        }
+        for (int b = 0; b < B; ++b) {
+            const float *dr = ds + ((size_t)b * p_out + p) * O;
+            const float g0 = v0 ? __ldg(dr + o0) : 0.f, g1 = v1 ? __ldg(dr + o1) : 0.f;
+#pragma unroll
+            for (int k = 0; k < PG_MAXN; ++k) {
+                if (q[k] != p_in) {                                    // warp-uniform
+                    const float *ur = u + ((size_t)b * p_in + q[k]) * MO;
+                    if (v0) a0[k] = fmaf(g0, __ldg(ur + j0), a0[k]);
+                    if (v1) a1[k] = fmaf(g1, __ldg(ur + j1), a1[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PG_MAXN; ++k) {
+            if (nb + k >= n_max) break;
+            red[w][j0] = a0[k];
+            red[w][j1] = a1[k];
+            __syncwarp();
+            if (lane < M) {
+                float t = 0.f;
+                if (q[k] != p_in)
+                    for (int o = 0; o < O; ++o) t += red[w][lane * O + o];
+                dAp[(size_t)(nb + k) * M + lane] = t;                   // padding slots: exactly 0
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// du through the reverse CSR: one warp per (input vertex, batch entry group).
+template <int NB>
+__global__ void __launch_bounds__(128)
+project_gather_du_kernel(const int32_t *__restrict__ rev_ptr, const int32_t *__restrict__ rev_slot,
+                         const float *__restrict__ ds, const float *__restrict__ A, float *__restrict__ du, int p_in,
+                         int p_out, int n_max, int B, int M, int O) {
+    const int MO = M * O, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x * 4 + w;
+    if (q >= p_in) return;
+    const int j0 = lane, j1 = lane + 32;
+    const bool v0 = j0 < MO, v1 = j1 < MO;
+    const int m0 = j0 / O, m1 = j1 / O, o0 = j0 % O, o1 = j1 % O;
+    const int e0 = __ldg(rev_ptr + q), e1 = __ldg(rev_ptr + q + 1);
+    for (int b0 = blockIdx.y * NB; b0 < B; b0 += gridDim.y * NB) {
+        float a0[NB], a1[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) a0[k] = a1[k] = 0.f;
+        for (int e = e0; e < e1; ++e) {
+            const int slot = __ldg(rev_slot + e);
+            const int p = slot / n_max;
+            const float c0 = v0 ? __ldg(A + (size_t)slot * M + m0) : 0.f, c1 = v1 ? __ldg(A + (size_t)slot * M + m1) : 0.f;
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                if (b0 + k < B) {
+                    const float *dr = ds + ((size_t)(b0 + k) * p_out + p) * O;
+                    if (v0) a0[k] = fmaf(c0, __ldg(dr + o0), a0[k]);
+                    if (v1) a1[k] = fmaf(c1, __ldg(dr + o1), a1[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            if (b0 + k < B) {
+                float *dst = du + ((size_t)(b0 + k) * p_in + q) * MO;
+                if (v0) dst[j0] = a0[k];
+                if (v1) dst[j1] = a1[k];
+            }
+        }
+    }
+}
+
+}  // namespace vcm
+
+extern "C" {
+
+int vcm_project_gather_fwd(const vcm_tables *h, const float *u, const float *A, float *s, int B, int M, int O,
+                           void *stream) {
+    const Tables *t = as_tables(h);
+    VCM_CHECK(t != nullptr, "tables handle is NULL");
+    VCM_CHECK(B > 0 && M > 0 && O > 0 && M * O <= 64, "project-first gather needs M*O <= 64 (got M=%d O=%d)", M, O);
+    VCM_DEVPTR(u); VCM_DEVPTR(A); VCM_DEVPTR(s);
+    if (t->p_out == 0) return VCM_OK;
+    dim3 grid((unsigned)ceil_div(t->p_out, 4), (unsigned)ceil_div(B, 4));
+    project_gather_fwd_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(t->idx, u, A, s, t->p_in, t->p_out, t->n_max, B,
+                                                                         M, O);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+int vcm_project_gather_bwd(const vcm_tables *h, const float *ds, const float *u, const float *A, float *dA, float *du,
+                           int B, int M, int O, void *stream) {
+    const Tables *t = as_tables(h);
+    VCM_CHECK(t != nullptr, "tables handle is NULL");
+    VCM_CHECK(B > 0 && M > 0 && O > 0 && M * O <= 64 && M <= 32, "project-first gather needs M*O <= 64");
+    VCM_DEVPTR(ds); VCM_DEVPTR(A); VCM_DEVPTR_OPT(u); VCM_DEVPTR_OPT(dA); VCM_DEVPTR_OPT(du);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dA != nullptr && t->p_out > 0) {
+        VCM_CHECK(u != nullptr, "u is required for dA");
+        project_gather_dA_kernel<<<(unsigned)ceil_div(t->p_out, 4), 128, 0, st>>>(t->idx, ds, u, dA, t->p_in, t->p_out,
+                                                                                  t->n_max, B, M, O);
+        VCM_LAUNCH_CHECK();
+    }
+    if (du != nullptr && t->p_in > 0) {
+        dim3 grid((unsigned)ceil_div(t->p_in, 4), (unsigned)ceil_div(B, 4));
+        project_gather_du_kernel<4><<<grid, 128, 0, st>>>(t->rev_ptr, t->rev_slot, ds, A, du, t->p_in, t->p_out, t->n_max,
+                                                          B, M, O);
+        VCM_LAUNCH_CHECK();
+    }
+    return VCM_OK;
+}
+
+}  // extern "C"

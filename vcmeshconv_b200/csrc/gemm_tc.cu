@@ -372,6 +372,7 @@ __global__ void sum_partials_kernel(const float *__restrict__ part, float *__res
     const size_t e4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (e4 >= n) return;
     float4 a = ldg4(part + e4);
+#pragma unroll 8
     for (int k = 1; k < n_split; ++k) {
         const float4 b = ldg4(part + (size_t)k * n + e4);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
@@ -467,6 +468,7 @@ DwSplit plan_dw_tc(int64_t R, int K, int O) {
     // row reduction so that ~1.5 waves of CTAs exist (partials are summed in fixed order afterwards).
     int64_t split = tiles * 10 >= (int64_t)sm_count() * 7 ? 1 : ceil_div(3 * (int64_t)sm_count(), 2 * tiles);
     if (split > s.num_kb / 2) split = s.num_kb / 2;
+    if (split > 24) split = 24;                        // the fixed-order second pass reads every slab
     if (split < 1) split = 1;
     s.kb_per_split = (int)ceil_div(s.num_kb, split);
     s.n_split = (int)ceil_div(s.num_kb, s.kb_per_split);

@@ -119,6 +119,42 @@ class _GatherContract(torch.autograd.Function):
         return dx, (dA if need_dA and not direct_dA else None), None
 
 
+class _ProjectGather(torch.autograd.Function):
+    """s[b,p,o] = sum_{n,m} A[p,n,m] u[b, idx[p,n], m, o] (project-first order, M*O <= 64)."""
+
+    @staticmethod
+    def forward(ctx, u, A, tables, M, O):
+        u, A = _req(u, "u"), _req(A, "coefficients")
+        B = u.shape[0]
+        if tuple(u.shape) != (B, tables.p_in, M * O) or tuple(A.shape) != (tables.p_out, tables.n_max, M):
+            raise RuntimeError("project-first gather shape mismatch: u %s A %s" % (tuple(u.shape), tuple(A.shape)))
+        s = torch.empty(B, tables.p_out, O, device=u.device, dtype=torch.float32)
+        nnz = tables.nnz
+        _lib.call("vcm_project_gather_fwd", tables.handle, _ptr(u), _ptr(A), _ptr(s), B, M, O, _lib.stream_ptr(),
+                  nbytes=4 * (B * nnz * M * O + nnz * M + nnz + s.numel()), flops=2 * B * nnz * M * O,
+                  tag="P%d>%d MO%d" % (tables.p_in, tables.p_out, M * O))
+        ctx.save_for_backward(u, A)
+        ctx.tables, ctx.cfg = tables, (M, O)
+        ctx.dA_target = _grad_target(A) if A.requires_grad else None
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        u, A = ctx.saved_tensors
+        t, (M, O) = ctx.tables, ctx.cfg
+        B = u.shape[0]
+        need_du, need_dA = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ds = _req(ds, "ds")
+        direct = need_dA and ctx.dA_target is not None
+        dA = (ctx.dA_target if direct else torch.empty_like(A)) if need_dA else None
+        du = torch.empty_like(u) if need_du else None
+        nnz = t.nnz
+        _lib.call("vcm_project_gather_bwd", t.handle, _ptr(ds), _ptr(u), _ptr(A), _ptr(dA), _ptr(du), B, M, O,
+                  _lib.stream_ptr(), nbytes=4 * (B * nnz * M * O + 2 * nnz * M + ds.numel() + (du.numel() if need_du else 0)),
+                  flops=2 * (int(need_du) + int(need_dA)) * B * nnz * M * O, tag="P%d>%d MO%d" % (t.p_in, t.p_out, M * O))
+        return du, (None if direct or not need_dA else dA), None, None, None
+
+
 class _BasisGemm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, W, bias, res, M, I, O, act, scale_y, scale_res, precision):
@@ -300,6 +336,11 @@ class _EdgeWeights(torch.autograd.Function):
 def gather_contract(x, coeffs, tables):
     """z[b,p,m*I+i] = sum_n coeffs[p,n,m] * x[b, idx[p,n], i] over real neighbours."""
     return _GatherContract.apply(x, coeffs, tables)
+
+
+def project_gather(u, coeffs, tables, M, O):
+    """s[b,p,o] = sum_{n,m} coeffs[p,n,m] * u[b, idx[p,n], m*O+o] (needs M*O <= 64)."""
+    return _ProjectGather.apply(u, coeffs, tables, M, O)
 
 
 def basis_gemm(z, weights, bias, res, M, I, O, act, scale_y=1.0, scale_res=0.0, precision=None):

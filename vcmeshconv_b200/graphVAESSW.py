@@ -134,9 +134,13 @@ class LASMConvssw(nn.Module):
         M, I, O = self.weight_num, self.in_channel, self.out_channel
         # u[b,q,m,:] = W_m x[b,q,:]: one GEMM with the bases stacked along the output axis ([1][M*O][I] view)
         u = F_.basis_gemm(in_pc, self.weights.view(1, M * O * I), None, None, 1, I, M * O, False)
-        tx = self.tables_expanded(in_pc.device)
-        s = F_.gather_contract(u.view(B, self.in_point_num * M, O),
-                               raw_w_weights.reshape(self.out_point_num, self.max_neighbor_num * M, 1), tx)
+        t = self.tables(in_pc.device)
+        if M * O <= 64:
+            s = F_.project_gather(u, raw_w_weights, t, M, O)
+        else:                                     # generic: an M = 1 gather over the basis-expanded table
+            tx = self.tables_expanded(in_pc.device)
+            s = F_.gather_contract(u.view(B, self.in_point_num * M, O),
+                                   raw_w_weights.reshape(self.out_point_num, self.max_neighbor_num * M, 1), tx)
         res, sy, sr = self._residual(in_pc, self.tables(in_pc.device))
         return F_.bias_act(s, self.bias, res, not is_final_layer, sy, sr)
 
