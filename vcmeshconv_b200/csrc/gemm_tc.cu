@@ -100,6 +100,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
+// smem tile -> global through the TMA engine (full-line, asynchronous stores; out-of-range rows/columns clipped)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                  "r"(ncols)
@@ -173,11 +187,17 @@ __device__ __forceinline__ float elu1(float t) { return t > 0.f ? t : expm1f(t);
 // STAGES: depth of the TMA -> MMA ring. Long reductions (K2, K4) use 4 stages and own the SM; the dz GEMM
 // has a short reduction (O/32 <= 16 k-blocks) and a large output tile, so it runs with 2 stages and two CTAs
 // per SM: one CTA's epilogue stores overlap the other's loads and MMAs.
-template <int BN, int MODE, int STAGES>
+// RT: 128-row tiles per CTA sharing one B tile (RT = 2: a 256 x BN output tile in two TMEM accumulators).
+// The dz GEMM is bound by operand re-reads from L2 (its reduction is short, its output huge); two row
+// tiles per B tile cut that traffic by a third.
+template <int BN, int MODE, int STAGES, int RT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const TcParams p) {
     constexpr int B_BYTES = BN * TK * 4;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int STAGE_BYTES = RT * A_BYTES + B_BYTES;
+    static_assert(RT == 1 || MODE != MODE_DW, "row-tile pairing is for the row-major GEMMs");
+    static_assert(RT * BN <= 512, "TMEM has 512 columns");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms (8 rows x 128 B)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -201,7 +221,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(tmem_slot, BN);
+    if (warp == 2) tmem_alloc(tmem_slot, RT * BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -217,7 +237,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
             mbar_wait(&empty[s], ph ^ 1u);
             mbar_expect_tx(&full[s], STAGE_BYTES);
-            const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+            const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + RT * A_BYTES;
             const int kb = kb_begin + it;
             if (MODE == MODE_DW) {
                 // A: z  as (32 kz, r, kz-block): box (32, 32 r, 4 blocks)   -> [4][32 r][32]
@@ -226,7 +246,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tma_load_3d(b_dst, &map_b, &full[s], 0, kb * TK, n_tile * (BN / 32));
             } else {
                 // A: row-major activations [R][Kred]: box (32 k, 128 r)
-                tma_load_2d(a_dst, &map_a, &full[s], kb * TK, m_tile * TM);
+#pragma unroll
+                for (int t = 0; t < RT; ++t)
+                    tma_load_2d(a_dst + t * A_BYTES, &map_a, &full[s], kb * TK, (m_tile * RT + t) * TM);
                 // B: (inner 32, rows, basis): FWD cuts W[m][o][i]; DZ reads Wt[k][o] with one "basis"
                 const int m = kb / p.kb_per_m;
                 tma_load_3d(b_dst, &map_b, &full[s], (kb - m * p.kb_per_m) * TK, n_tile * BN, m);
@@ -240,9 +262,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            const uint32_t a_base = smem_base + s * STAGE_BYTES, b_base = a_base + A_BYTES;
+            const uint32_t a_base = smem_base + s * STAGE_BYTES, b_base = a_base + RT * A_BYTES;
 #pragma unroll
-            for (int j = 0; j < TK / 8; ++j) {
+            for (int tj = 0; tj < RT * (TK / 8); ++tj) {
+                const int t = tj / (TK / 8), j = tj % (TK / 8);
                 uint64_t da, db;
                 if (MODE == MODE_DW) {
                     // MN-major tf32 only exists as SWIZZLE_128B_BASE32B (32-byte chunks XOR row % 4, written by
@@ -252,10 +275,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     db = make_desc(b_base + j * 1024, 4096, 512, LT_SW128_32B);
                 } else {
                     // K-major SW128: 8-row groups 1024 B apart (SBO); k advances 32 B inside the swizzle row
-                    da = make_desc(a_base + j * 32, 16, 1024);
+                    da = make_desc(a_base + t * A_BYTES + j * 32, 16, 1024);
                     db = make_desc(b_base + j * 32, 16, 1024);
                 }
-                umma_tf32(tmem_base, da, db, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                umma_tf32(tmem_base + (uint32_t)(t * BN), da, db, idesc, (it > 0 || j > 0) ? 1u : 0u);
             }
             umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
         }
@@ -266,14 +289,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int row = q * 32 + lane;         // accumulator row owned by this thread
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        if (n_iter <= 0) {
-            // nothing was accumulated (empty split): contribute zeros
-        }
-        const int64_t gr = (int64_t)m_tile * TM + row;          // FWD/DZ: activation row; DW: kz
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int tc = 0; tc < RT * (BN / 32); ++tc) {
+            const int t = tc / (BN / 32), c = tc - t * (BN / 32);
+            const int64_t gr = ((int64_t)m_tile * RT + t) * TM + row;   // FWD/DZ: activation row; DW: kz
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c * 32), v);
             const int col0 = n_tile * BN + c * 32;
             if (MODE == MODE_FWD && p.partial != nullptr) {
                 if (gr < p.R && col0 < p.O) {
@@ -308,12 +329,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             } else if (MODE == MODE_DZ) {
-                if (gr < p.R && col0 < p.K) {                   // K % 32 == 0: whole chunk in range
-                    float *dst = p.out + (size_t)gr * p.K + col0;
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4)
-                        st4(dst + 4 * j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+                // dz is the big output of the backward pass: stage the 128 x 32 chunk in (free) pipeline smem
+                // in the 128B-swizzled layout and let the TMA engine write it as full lines, asynchronously.
+                // A lane = row register layout stored directly would be 32-way address-divergent.
+                const uint32_t stage_buf = smem_base + (uint32_t)(tc & 1) * A_BYTES;
+                if (tc >= 2) {                                    // the buffer's previous TMA store has read it
+                    if (threadIdx.x == 128) tma_store_wait_read<1>();
+                    epilogue_bar();
                 }
+                const uint32_t rowaddr = stage_buf + (uint32_t)row * 128u;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((j4 ^ (row & 7)) << 4)),
+                                 "f"(v[4 * j4]), "f"(v[4 * j4 + 1]), "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3])
+                                 : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                epilogue_bar();
+                if (threadIdx.x == 128) tma_store_2d(&map_c, stage_buf, col0, (int)(((int64_t)m_tile * RT + t) * TM));
             } else {
                 // Written in dW's native [M][O][I] layout (lanes = consecutive kz = consecutive i of one basis,
                 // so every store below is one 128-byte line); with a split reduction each split owns one such
@@ -326,12 +358,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
+        if (MODE == MODE_DZ && threadIdx.x == 128) tma_store_wait_all();
         tc_fence_before();
     }
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, RT * BN);
     }
 }
 
@@ -437,14 +470,15 @@ int pick_bn(int n) {       // n % 32 == 0
     return 32;
 }
 
-template <int MODE, int STAGES>
-int launch(int bn, dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, cudaStream_t st) {
+template <int MODE, int STAGES, int RT = 1>
+int launch(int bn, dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, const TcParams &p,
+           cudaStream_t st) {
 #define VCM_TC_CASE(BN_)                                                                                          \
     case BN_: {                                                                                                   \
-        auto k = tc_gemm_kernel<BN_, MODE, STAGES>;                                                               \
-        const int smem = STAGES * (A_BYTES + BN_ * TK * 4) + 1024 + 256;                                          \
+        auto k = tc_gemm_kernel<BN_, MODE, STAGES, RT>;                                                           \
+        const int smem = STAGES * (RT * A_BYTES + BN_ * TK * 4) + 1024 + 256;                                     \
         VCM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
-        k<<<grid, NTHREADS, smem, st>>>(ma, mb, p);                                                               \
+        k<<<grid, NTHREADS, smem, st>>>(ma, mb, mc, p);                                                           \
         break;                                                                                                    \
     }
     switch (bn) {
@@ -530,7 +564,7 @@ int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_poin
     p.bias = bias; p.res = res; p.y_act = y_act; p.out = out; p.per_point = per_point; p.act = act; p.sy = sy; p.sr = sr;
     p.partial = n_split > 1 ? ws : nullptr;
     dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(O, bn), (unsigned)n_split);
-    if (int e = launch<MODE_FWD, 4>(bn, grid, ma, mb, p, st)) return e;
+    if (int e = launch<MODE_FWD, 4>(bn, grid, ma, mb, ma, p, st)) return e;
     if (n_split > 1) {
         splitk_fwd_epilogue_kernel<<<(unsigned)ceil_div(R * O / 4, 256), 256, 0, st>>>(ws, n_split, R, O, P_out, bias,
                                                                                       per_point, res, y_act, out, act,
@@ -566,8 +600,20 @@ int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64
     p.R = R; p.K = K; p.O = O; p.I = I;
     p.num_kb = O / TK; p.kb_per_m = p.num_kb; p.kb_per_split = p.num_kb;
     p.out = dz;
+    CUtensorMap mc;                                   // store map over dz [R][K]: box (32 columns, 128 rows)
+    {
+        const uint64_t d[2] = {(uint64_t)K, (uint64_t)R}, s2[2] = {4, (uint64_t)K * 4};
+        const uint32_t b[2] = {TK, TM};
+        if (int e = make_map(&mc, dz, 2, d, s2, b)) return e;
+    }
+    // enough tiles to fill the machine twice: pair row tiles (256 x BN per CTA, one B tile for both)
+    static const bool pair = [] { const char *e = getenv("VCM_DZ_PAIR"); return e && atoi(e) != 0; }();
+    if (pair && ceil_div(R, 2 * TM) * ceil_div(K, bn) >= 2 * (int64_t)sm_count()) {
+        dim3 grid2((unsigned)ceil_div(R, 2 * TM), (unsigned)ceil_div(K, bn), 1);
+        return launch<MODE_DZ, 2, 2>(bn, grid2, ma, mb, mc, p, st);
+    }
     dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(K, bn), 1);
-    return launch<MODE_DZ, 2>(bn, grid, ma, mb, p, st);
+    return launch<MODE_DZ, 2>(bn, grid, ma, mb, mc, p, st);
 }
 
 size_t tc_basis_bwd_dw_workspace(int64_t R, int M, int I, int O, int precision) {
@@ -598,7 +644,7 @@ int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64
     p.direct = sp.n_split == 1;
     p.out = p.direct ? dW : ws;
     dim3 grid((unsigned)ceil_div(K, TM), (unsigned)ceil_div(O, bn), (unsigned)sp.n_split);
-    if (int e = launch<MODE_DW, 4>(bn, grid, ma, mb, p, st)) return e;
+    if (int e = launch<MODE_DW, 4>(bn, grid, ma, mb, ma, p, st)) return e;
     if (p.direct) return VCM_OK;
     const size_t n = (size_t)K * O;
     sum_partials_kernel<<<(unsigned)ceil_div((int64_t)(n / 4), 256), 256, 0, st>>>(ws, dW, n, sp.n_split);
