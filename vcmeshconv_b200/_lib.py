@@ -69,7 +69,7 @@ class VcmError(RuntimeError):
 def lib():
     global _lib
     if _lib is None:
-        path = _build.LIB_CUDA
+        path = os.environ.get("VCM_LIBRARY") or _build.LIB_CUDA      # override: A/B runs of two builds
         if not os.path.exists(path):
             _build.build_cuda()          # raises if nvcc is unavailable: no fallback
         L = C.CDLL(path)

@@ -304,6 +304,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         st4(dst + 4 * j4, make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
                 }
             } else if (MODE == MODE_FWD) {
+                // lane = accumulator row: each thread streams its own row segment (bias, residual, y, out). The
+                // rows of a warp are O*4 bytes apart, i.e. one dense region for these layer widths; a transposed,
+                // lane = column variant was measured slower in the full step (profiles/README.md).
                 if (gr < p.R && col0 < p.O) {
                     const size_t at = (size_t)gr * p.O + col0;
                     const float *bp = p.bias ? p.bias + (p.per_point ? (size_t)(gr % p.P_out) * p.O : 0) + col0 : nullptr;
@@ -493,17 +496,44 @@ int launch(int bn, dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, cons
     return VCM_OK;
 }
 
+// Split count that wastes the least machine time to wave quantisation: CTAs = tiles * split run in
+// ceil(CTAs / slots) waves of `slots` concurrent CTAs; every CTA works through num_kb / split k-blocks.
+int tune_flag(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+int best_split(int64_t tiles, int num_kb, int max_split, int slots) {
+    if (max_split < 1) max_split = 1;
+    double best_cost = 1e30;
+    int best = 1;
+    for (int s = 1; s <= max_split; ++s) {
+        const int64_t per = ceil_div(num_kb, s);
+        const int64_t eff_s = ceil_div(num_kb, per);                 // splits that actually get work
+        const int64_t waves = ceil_div(tiles * eff_s, slots);
+        const double cost = (double)waves * (double)(per + 6);       // + fixed per-CTA prologue/epilogue
+        if (cost < best_cost * 0.97) { best_cost = cost; best = (int)eff_s; }
+    }
+    return best;
+}
+
 struct DwSplit { int n_split, kb_per_split, num_kb; };
 DwSplit plan_dw_tc(int64_t R, int K, int O) {
     DwSplit s;
     s.num_kb = (int)ceil_div(R, TK);
     const int64_t tiles = ceil_div(K, TM) * ceil_div(O, pick_bn(O));
-    // enough output tiles to fill the machine: one pass, written straight into dW. Otherwise split the
-    // row reduction so that ~1.5 waves of CTAs exist (partials are summed in fixed order afterwards).
-    int64_t split = tiles * 10 >= (int64_t)sm_count() * 7 ? 1 : ceil_div(3 * (int64_t)sm_count(), 2 * tiles);
-    if (split > s.num_kb / 2) split = s.num_kb / 2;
-    if (split > 24) split = 24;                        // the fixed-order second pass reads every slab
-    if (split < 1) split = 1;
+    // Enough output tiles to fill the machine: one pass, written straight into dW. Otherwise split the row
+    // reduction (wave-quantisation aware; partial slabs are summed in fixed order afterwards).
+    int64_t split = 1;
+    static const int policy = tune_flag("VCM_SPLIT_POLICY", 1);
+    if (policy == 0) {
+        split = tiles * 10 >= (int64_t)sm_count() * 7 ? 1 : ceil_div(3 * (int64_t)sm_count(), 2 * tiles);
+        if (split > s.num_kb / 2) split = s.num_kb / 2;
+        if (split > 24) split = 24;
+        if (split < 1) split = 1;
+    } else if (tiles < 2 * (int64_t)sm_count()) {
+        split = best_split(tiles, s.num_kb, s.num_kb / 2 < 24 ? s.num_kb / 2 : 24, sm_count());
+    }
     s.kb_per_split = (int)ceil_div(s.num_kb, split);
     s.n_split = (int)ceil_div(s.num_kb, s.kb_per_split);
     return s;
@@ -527,10 +557,15 @@ bool tc_supported(int which, int64_t R, int M, int I, int O, int precision) {
 static int fwd_splits(int64_t R, int K, int O) {
     const int64_t tiles = ceil_div(R, TM) * ceil_div(O, pick_bn(O));
     const int num_kb = K / TK;
-    if (tiles * 2 > sm_count() || num_kb < 16) return 1;
-    int64_t split = ceil_div((int64_t)sm_count(), tiles);
-    if (split > num_kb / 4) split = num_kb / 4;
-    return split < 1 ? 1 : (int)split;
+    static const int policy = tune_flag("VCM_SPLIT_POLICY", 1);
+    if (policy == 0) {
+        if (tiles * 2 > sm_count() || num_kb < 16) return 1;
+        int64_t split = ceil_div((int64_t)sm_count(), tiles);
+        if (split > num_kb / 4) split = num_kb / 4;
+        return split < 1 ? 1 : (int)split;
+    }
+    if (tiles >= 2 * (int64_t)sm_count() || num_kb < 16) return 1;
+    return best_split(tiles, num_kb, num_kb / 4 < 32 ? num_kb / 4 : 32, sm_count());
 }
 
 size_t tc_basis_fwd_workspace(int64_t R, int M, int I, int O) {
