@@ -337,39 +337,49 @@ scatter_rev_kernel(const int32_t *__restrict__ rev_ptr, const int32_t *__restric
 }
 
 // ------------------------------------------------- residual edge weights ----
+// one warp per output vertex, lanes over the neighbour slots (fixed-order butterfly sums)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
 __global__ void edge_weights_fwd_kernel(const int32_t *__restrict__ idx, const float *__restrict__ p_nb,
                                         float *__restrict__ pn, int p_in, int p_out, int n_max) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (p >= p_out) return;
     const int32_t *ir = idx + (size_t)p * n_max;
     const float *pr = p_nb + (size_t)p * n_max;
     float s = 0.f;
-    for (int n = 0; n < n_max; ++n) s += ir[n] != p_in ? fabsf(pr[n]) : 0.f;
-    s += 1e-8f;
-    for (int n = 0; n < n_max; ++n) pn[(size_t)p * n_max + n] = ir[n] != p_in ? fabsf(pr[n]) / s : 0.f;
+    for (int n = lane; n < n_max; n += 32) s += __ldg(ir + n) != p_in ? fabsf(__ldg(pr + n)) : 0.f;
+    s = warp_sum(s) + 1e-8f;
+    for (int n = lane; n < n_max; n += 32)
+        pn[(size_t)p * n_max + n] = __ldg(ir + n) != p_in ? fabsf(__ldg(pr + n)) / s : 0.f;
 }
 
 __global__ void edge_weights_bwd_kernel(const int32_t *__restrict__ idx, const float *__restrict__ p_nb,
                                         const float *__restrict__ dpn, float *__restrict__ dp, int p_in, int p_out,
                                         int n_max) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (p >= p_out) return;
     const int32_t *ir = idx + (size_t)p * n_max;
     const float *pr = p_nb + (size_t)p * n_max;
     const float *gr = dpn + (size_t)p * n_max;
     float s = 0.f, dot = 0.f;
-    for (int n = 0; n < n_max; ++n)
-        if (ir[n] != p_in) {
-            s += fabsf(pr[n]);
-            dot += gr[n] * fabsf(pr[n]);
+    for (int n = lane; n < n_max; n += 32)
+        if (__ldg(ir + n) != p_in) {
+            const float a = fabsf(__ldg(pr + n));
+            s += a;
+            dot += __ldg(gr + n) * a;
         }
-    s += 1e-8f;
-    dot /= s;                                              // sum_k dpn[k] * pn[k]
-    for (int n = 0; n < n_max; ++n) {
+    s = warp_sum(s) + 1e-8f;
+    dot = warp_sum(dot) / s;                               // sum_k dpn[k] * pn[k]
+    for (int n = lane; n < n_max; n += 32) {
         float v = 0.f;
-        if (ir[n] != p_in) {
-            const float sg = pr[n] > 0.f ? 1.f : (pr[n] < 0.f ? -1.f : 0.f);
-            v = sg * (gr[n] - dot) / s;
+        if (__ldg(ir + n) != p_in) {
+            const float w = __ldg(pr + n);
+            const float sg = w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f);
+            v = sg * (__ldg(gr + n) - dot) / s;
         }
         dp[(size_t)p * n_max + n] = v;
     }
@@ -549,7 +559,7 @@ int vcm_edge_weights_fwd(const vcm_tables *h, const float *p_nb, float *pn, void
     VCM_CHECK(t != nullptr, "tables handle is NULL");
     VCM_DEVPTR(p_nb); VCM_DEVPTR(pn);
     if (t->p_out == 0 || t->n_max == 0) return VCM_OK;
-    edge_weights_fwd_kernel<<<(unsigned)ceil_div(t->p_out, 128), 128, 0, (cudaStream_t)stream>>>(
+    edge_weights_fwd_kernel<<<(unsigned)ceil_div((int64_t)t->p_out * 32, 128), 128, 0, (cudaStream_t)stream>>>(
         t->idx, p_nb, pn, t->p_in, t->p_out, t->n_max);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
@@ -560,7 +570,7 @@ int vcm_edge_weights_bwd(const vcm_tables *h, const float *p_nb, const float *dp
     VCM_CHECK(t != nullptr, "tables handle is NULL");
     VCM_DEVPTR(p_nb); VCM_DEVPTR(dpn); VCM_DEVPTR(dp);
     if (t->p_out == 0 || t->n_max == 0) return VCM_OK;
-    edge_weights_bwd_kernel<<<(unsigned)ceil_div(t->p_out, 128), 128, 0, (cudaStream_t)stream>>>(
+    edge_weights_bwd_kernel<<<(unsigned)ceil_div((int64_t)t->p_out * 32, 128), 128, 0, (cudaStream_t)stream>>>(
         t->idx, p_nb, dpn, dp, t->p_in, t->p_out, t->n_max);
     VCM_LAUNCH_CHECK();
     return VCM_OK;

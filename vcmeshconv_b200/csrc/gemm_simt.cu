@@ -234,7 +234,8 @@ __global__ void reduce_dw_kernel(const float *__restrict__ part, float *__restri
     dW[((size_t)m * O + o) * I + i] = s;
 }
 
-// ds / dbias / dres in one pass; one thread per (p, o), loop over the batch.
+// ds / dbias / dres in one pass; one thread per (p, o), loop over the batch. The batch loop is blocked by 8
+// with all loads issued first: these tensors are small, the kernel is latency-bound, not bandwidth-bound.
 __global__ void act_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ y, float *__restrict__ ds,
                                float *__restrict__ dbias, float *__restrict__ dres, int B, int P_out, int O, int act,
                                float sy, float sr) {
@@ -242,17 +243,26 @@ __global__ void act_bwd_kernel(const float *__restrict__ dout, const float *__re
     const size_t PO = (size_t)P_out * O;
     if (e >= PO) return;
     float sum = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const size_t at = (size_t)b * PO + e;
-        const float g = __ldg(dout + at);
-        float d = g * sy;
-        if (act) {
-            const float yy = __ldg(y + at);
-            d = yy > 0.f ? d : d * (yy + 1.f);
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        float g[8], yy[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool in = b0 + u < B;
+            const size_t at = (size_t)(b0 + u) * PO + e;
+            g[u] = in ? __ldg(dout + at) : 0.f;
+            yy[u] = (in && act) ? __ldg(y + at) : 1.f;
         }
-        ds[at] = d;
-        sum += d;
-        if (dres) dres[at] = g * sr;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (b0 + u < B) {
+                const size_t at = (size_t)(b0 + u) * PO + e;
+                float d = g[u] * sy;
+                if (act) d = yy[u] > 0.f ? d : d * (yy[u] + 1.f);
+                ds[at] = d;
+                sum += d;                                   // fixed order b = 0..B-1
+                if (dres) dres[at] = g[u] * sr;
+            }
+        }
     }
     if (dbias) dbias[e] = sum;
 }
