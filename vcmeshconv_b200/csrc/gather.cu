@@ -429,10 +429,18 @@ static int plan_grad(const Tables *t, int B, int I, GradPlan *pl) {
     while (g.TP > 1 && bytes(g.TP) > (size_t)kMaxSmem) { g.TP /= 2; g.CB *= 2; }
     if (bytes(g.TP) > (size_t)kMaxSmem)
         return fail(VCM_EUNSUPPORTED, "neighbour count %d too large for the staging buffer", t->n_max);
+    // Column passes of a vertex are split over CTAs (grid.y) when there are few vertices; pick the split that
+    // loses the least time to wave quantisation: CTAs run in waves of 2 per SM, each does `passes` passes
+    // (+ ~1 pass worth of staging and reduction).
     const int64_t bx = ceil_div(t->p_out, g.TP), total_passes = ceil_div(g.C, g.CB);
-    int64_t split = ceil_div(2 * (int64_t)sm_count(), bx > 0 ? bx : 1);
-    if (split > total_passes) split = total_passes;
-    if (split < 1) split = 1;
+    const int64_t slots = 2 * (int64_t)sm_count();
+    int64_t split = 1;
+    double best = 1e30;
+    for (int64_t s2 = 1; s2 <= total_passes; ++s2) {
+        const int64_t per = ceil_div(total_passes, s2), eff = ceil_div(total_passes, per);
+        const double cost = (double)ceil_div(bx * eff, slots) * (double)(per + 1);
+        if (cost < best * 0.97) { best = cost; split = eff; }
+    }
     pl->g = g;
     pl->passes = (int)ceil_div(total_passes, split);
     pl->n_split = (int)ceil_div(total_passes, pl->passes);
