@@ -110,6 +110,12 @@ VCM_API const int32_t *vcm_tables_device_ptr(const vcm_tables *t, int which);
 VCM_API int vcm_gather_contract_fwd(const vcm_tables *t, const float *x, const float *A, float *z,
                                     int B, int I, int M, void *stream);
 
+/* Same contraction with the arithmetic mode of the basis GEMMs: VCM_PREC_TF32 runs it on the tensor pipe
+ * (mma.sync m16n8k8 tf32, fp32 accumulate) when M <= 24 and I % 16 == 0; every other case is the fp32
+ * kernel above. */
+VCM_API int vcm_gather_contract_fwd_ex(const vcm_tables *t, const float *x, const float *A, float *z, int B,
+                                       int I, int M, int precision, void *stream);
+
 /* Project-first order for narrow outputs (M*O <= 64; the 32 -> 3 layer on the full mesh). With
  * u[b,q,m,o] = sum_i W[m,o,i] x[b,q,i] computed by vcm_basis_fwd (bases stacked along the output axis):
  *   fwd: s[b,p,o]    = sum_{n,m} A[p,n,m] u[b, idx[p,n], m, o]

@@ -159,3 +159,40 @@ def test_layer_in_tf32_mode_meets_stated_tolerance():
     assert rel_err(Ag.grad.cpu().numpy(), coeffs.grad.numpy()) < TF32_TOL
     for k, p in layer.named_parameters():
         assert rel_err(p.grad.cpu().numpy(), params[k].grad.numpy()) < TF32_TOL, k
+
+
+@pytest.mark.parametrize("cfg", [("pool1", 32, 17, 4), ("unpool1", 64, 17, 3), ("pool0", 128, 17, 2), ("pool1", 48, 5, 2),
+                                 ("unpool1", 16, 24, 1)], ids=lambda c: "%s_I%d_M%d_B%d" % c)
+def test_gather_contract_on_tensor_pipe(cfg):
+    """K1 in TF32 mode (mma.sync m16n8k8): exact vs the fp64 contraction of TF32-truncated operands, and within
+    the stated TF32 tolerance of the fp32 kernel."""
+    from vcmeshconv_b200 import connectivity
+    from vcmeshconv_b200 import graph_sampling as gs
+    from vcmeshconv_b200 import synthetic
+    import os
+    if os.environ.get("VCM_K1_MMA", "0") == "0":
+        pytest.skip("tensor-pipe K1 is opt-in (VCM_K1_MMA=1); the fp32 kernel is faster in the full step")
+    which, I, M, B = cfg
+    pts, faces = synthetic.sphere(1500, seed=2)
+    tabs, nums = gs.build_tables(faces, 1500, [(1, 1, 1), (2, 2, 2)])
+    table = tabs[which]
+    p_in = nums[2] if which.startswith("unpool") else nums[int(which[-1])]
+    t = connectivity.DeviceTables(table, p_in)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, p_in, I, device="cuda", generator=g)
+    A = torch.randn(t.p_out, t.n_max, M, device="cuda", generator=g)
+    z_tc = torch.full((B, t.p_out, M * I), float("nan"), device="cuda")
+    z_32 = torch.empty_like(z_tc)
+    L = _lib.lib()
+    _lib.check(L.vcm_gather_contract_fwd_ex(t.handle, x.data_ptr(), A.data_ptr(), z_tc.data_ptr(), B, I, M, TF32,
+                                            _lib.stream_ptr()))
+    _lib.check(L.vcm_gather_contract_fwd(t.handle, x.data_ptr(), A.data_ptr(), z_32.data_ptr(), B, I, M,
+                                         _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ids = torch.from_numpy(table[:, 1::2].astype("int64")).cuda()
+    mask = (ids != p_in).double()
+    xpad = torch.cat([trunc_tf32(x).double(), torch.zeros(B, 1, I, device="cuda", dtype=torch.float64)], 1)
+    want = torch.einsum("pnm,bpni->bpmi", trunc_tf32(A).double() * mask[:, :, None], xpad[:, ids]).reshape(B, t.p_out, M * I)
+    assert not torch.isnan(z_tc).any()
+    assert rel_err(z_tc.cpu().numpy(), want.cpu().numpy()) < EXACT_TOL
+    assert rel_err(z_tc.cpu().numpy(), z_32.cpu().numpy()) < TF32_TOL

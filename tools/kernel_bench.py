@@ -53,7 +53,7 @@ def main():
     nnz = t.nnz
     X, Z, Ab, Gb, Y, Wb = 4 * x.numel(), 4 * z.numel(), 4 * nnz * M, 4 * B * nnz * I, 4 * out.numel(), 4 * W.numel()
     calls = {
-        "k1": (lambda: L.vcm_gather_contract_fwd(t.handle, x.data_ptr(), A.data_ptr(), z.data_ptr(), B, I, M, st),
+        "k1": (lambda: L.vcm_gather_contract_fwd_ex(t.handle, x.data_ptr(), A.data_ptr(), z.data_ptr(), B, I, M, prec, st),
                X + Ab + 4 * nnz + Z, 2 * B * nnz * M * I),
         "k5": (lambda: L.vcm_coeff_grad(t.handle, dz.data_ptr(), x.data_ptr(), A.data_ptr(), dA.data_ptr(), dG.data_ptr(),
                                         ws.data_ptr(), B, I, M, st), Z + X + 2 * Ab + 4 * nnz + Gb, 4 * B * nnz * M * I),

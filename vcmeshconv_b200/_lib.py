@@ -35,6 +35,7 @@ SIGNATURES = {
     "vcm_tables_export": (_i, [_p, _i, _p, _sz]),
     "vcm_tables_device_ptr": (_p, [_p, _i]),
     "vcm_gather_contract_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "vcm_gather_contract_fwd_ex": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "vcm_project_gather_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "vcm_project_gather_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vcm_coeff_grad_workspace": (_sz, [_p, _i, _i, _i]),

@@ -781,3 +781,131 @@ int vcm_project_gather_bwd(const vcm_tables *h, const float *ds, const float *u,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// K1 on the tensor pipe (TF32 mode only). Per output vertex the contraction is a small GEMM
+//   D[c, m] = sum_n G[c, n] * A_p[n, m],   c = (b, i) columns of the vertex row, G[c, n] = x[b, idx[p,n], i]
+// with M = 17 and at most a few dozen neighbours: far below the 128-row tiles tcgen05 works on, and with a
+// different B operand (A_p) for every vertex, so UMMA tiles cannot be shared across vertices. Warp-level
+// mma.sync m16n8k8 (tf32 in, fp32 accumulate) fits exactly: 16 columns x 8 bases x 8 neighbours per instruction,
+// fragments taken straight from L2 (x, 32-byte segments per neighbour row) and shared memory (A_p). It replaces
+// ~70 FMA-pipe instructions per 16 columns and neighbour octet by 3 HMMA + 4 LDG + 6 LDS, needs ~40 registers
+// (32 warps per SM instead of 16) and leaves the kernel bound by the z store stream. Operands are fp32 bit
+// patterns (the tensor core reads the top 19 bits): same arithmetic class as the TF32 basis GEMMs.
+namespace vcm {
+
+constexpr int kMmaMS = 40;         // smem row stride of the coefficient tile: t*40 mod 32 = 0,8,16,24 -> conflict-free
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int MTILES>              // 8-wide basis tiles: 3 for M <= 24, 1 for M <= 8
+__global__ void __launch_bounds__(128, 8)
+gather_contract_fwd_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
+                               const float *__restrict__ x, const float *__restrict__ A, float *__restrict__ z,
+                               int p_in, int p_out, int n_max, int I, int M, int B, int tiles_per_cta) {
+    extern __shared__ __align__(16) float smem[];
+    const int slot = blockIdx.x;
+    const int2 meta = __ldg(meta_sorted + slot);
+    const int p = meta.x, l = meta.y;
+    const int n_pad = (l + 7) & ~7;
+    float *A_s = smem;                                              // [n_pad][kMmaMS], zero padded
+    int32_t *idx_s = reinterpret_cast<int32_t *>(smem + (size_t)((n_max + 7) & ~7) * kMmaMS);   // [n_pad], -1 = no row
+    const int tid = threadIdx.x;
+    for (int e = tid; e < n_pad * kMmaMS; e += 128) {
+        const int n = e / kMmaMS, m = e - n * kMmaMS;
+        A_s[e] = (n < l && m < M) ? __ldg(A + ((size_t)p * n_max + n) * M + m) : 0.f;
+    }
+    for (int n = tid; n < n_pad; n += 128) {
+        const int q = n < l ? __ldg(idx_sorted + (size_t)slot * n_max + n) : p_in;
+        idx_s[n] = q == p_in ? -1 : q;
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int tiles_per_b = I >> 4, n_tiles = B * tiles_per_b;
+    const int tile_end = min(n_tiles, (int)(blockIdx.y + 1) * tiles_per_cta);
+    float *zp = z + (size_t)p * M * I;
+    for (int ct = blockIdx.y * tiles_per_cta + warp; ct < tile_end; ct += 4) {
+        const int b = ct / tiles_per_b, i0 = (ct - b * tiles_per_b) << 4;
+        const float *xb = x + (size_t)b * p_in * I + i0 + g;
+        float acc[MTILES][4];
+#pragma unroll
+        for (int mt = 0; mt < MTILES; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+#pragma unroll 2
+        for (int ks = 0; ks < n_pad; ks += 8) {
+            const int q_lo = idx_s[ks + t], q_hi = idx_s[ks + t + 4];
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            if (q_lo >= 0) {
+                const float *r = xb + (size_t)q_lo * I;
+                a0 = __float_as_uint(__ldg(r));
+                a1 = __float_as_uint(__ldg(r + 8));
+            }
+            if (q_hi >= 0) {
+                const float *r = xb + (size_t)q_hi * I;
+                a2 = __float_as_uint(__ldg(r));
+                a3 = __float_as_uint(__ldg(r + 8));
+            }
+            const float *Alo = A_s + (ks + t) * kMmaMS + g, *Ahi = Alo + 4 * kMmaMS;
+#pragma unroll
+            for (int mt = 0; mt < MTILES; ++mt)
+                mma_tf32_16x8x8(acc[mt], a0, a1, a2, a3, __float_as_uint(Alo[mt * 8]), __float_as_uint(Ahi[mt * 8]));
+        }
+        float *zr = zp + (size_t)b * p_out * M * I + i0 + g;
+#pragma unroll
+        for (int mt = 0; mt < MTILES; ++mt) {
+            const int m0 = mt * 8 + 2 * t;
+            if (m0 < M) {
+                zr[(size_t)m0 * I] = acc[mt][0];
+                zr[(size_t)m0 * I + 8] = acc[mt][2];
+            }
+            if (m0 + 1 < M) {
+                zr[(size_t)(m0 + 1) * I] = acc[mt][1];
+                zr[(size_t)(m0 + 1) * I + 8] = acc[mt][3];
+            }
+        }
+    }
+}
+
+}  // namespace vcm
+
+extern "C" int vcm_gather_contract_fwd_ex(const vcm_tables *h, const float *x, const float *A, float *z, int B, int I,
+                                          int M, int precision, void *stream) {
+    using namespace vcm;
+    const Tables *t = as_tables(h);
+    // opt-in: correct (tests/test_gpu_gemm_tc.py) but measured 1.5 % slower than the fp32 kernel in the full
+    // training step (3.675 vs 3.618 ms, same box): K1 is bound by its memory system, not by the FMA pipe
+    static const int use_mma = [] { const char *e = getenv("VCM_K1_MMA"); return e ? atoi(e) : 0; }();
+    if (precision != VCM_PREC_TF32 || !use_mma || t == nullptr || M > 24 || M < 2 || (I & 15) != 0 || B <= 0 ||
+        t->p_out == 0)
+        return vcm_gather_contract_fwd(h, x, A, z, B, I, M, stream);
+    VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR(z);
+    const int n_tiles = B * (I >> 4);
+    // ~2 CTAs of 4 warps per SM slot set, each warp several column tiles
+    int64_t want = ceil_div(8 * (int64_t)sm_count(), t->p_out);
+    if (want < 1) want = 1;
+    int64_t gy = want < ceil_div(n_tiles, 4) ? want : ceil_div(n_tiles, 4);
+    const int tiles_per_cta = (int)(ceil_div(ceil_div(n_tiles, gy), 4) * 4);
+    gy = ceil_div(n_tiles, tiles_per_cta);
+    const size_t smem = ((size_t)((t->n_max + 7) & ~7) * (kMmaMS + 1)) * sizeof(float);
+    dim3 grid((unsigned)t->p_out, (unsigned)gy);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M <= 8) {
+        auto k = gather_contract_fwd_mma_kernel<1>;
+        if (int e = set_smem(k, smem)) return e;
+        k<<<grid, 128, smem, st>>>(t->idx_sorted, reinterpret_cast<const int2 *>(t->meta_sorted), x, A, z, t->p_in, t->p_out,
+                                   t->n_max, I, M, B, tiles_per_cta);
+    } else {
+        auto k = gather_contract_fwd_mma_kernel<3>;
+        if (int e = set_smem(k, smem)) return e;
+        k<<<grid, 128, smem, st>>>(t->idx_sorted, reinterpret_cast<const int2 *>(t->meta_sorted), x, A, z, t->p_in, t->p_out,
+                                   t->n_max, I, M, B, tiles_per_cta);
+    }
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}

@@ -80,7 +80,8 @@ class _GatherContract(torch.autograd.Function):
         z = torch.empty(B, tables.p_out, M * I, device=x.device, dtype=torch.float32)
         if B:
             nnz = tables.nnz
-            _lib.call("vcm_gather_contract_fwd", tables.handle, _ptr(x), _ptr(A), _ptr(z), B, I, M, _lib.stream_ptr(),
+            _lib.call("vcm_gather_contract_fwd_ex", tables.handle, _ptr(x), _ptr(A), _ptr(z), B, I, M, _precision,
+                      _lib.stream_ptr(),
                       nbytes=4 * (x.numel() + nnz * M + nnz + z.numel()), flops=2 * B * nnz * M * I,
                       tag="P%d>%d I%d M%d" % (p_in, tables.p_out, I, M))
         ctx.save_for_backward(x, A)
