@@ -73,6 +73,11 @@ __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<floa
 // streaming store: written once, consumed by a later kernel, keep it out of L1
 __device__ __forceinline__ void st4_cs(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
 
+// Packed fp32x2 FMA (FFMA2, new on sm_100): two IEEE fp32 FMAs per lane per issued instruction; results are
+// bit-identical to two scalar FMAs. The gather-side kernels are issue-bound, so halving their FMA count pays.
+__device__ __forceinline__ float2 fma2(float a, float2 b, float2 c) { return __ffma2_rn(make_float2(a, a), b, c); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 template <int VEC>
 struct Vec;
 template <>

@@ -108,10 +108,21 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx_sorted, const int2 *_
             const float4 t = a4[k];
             a[4 * k] = t.x; a[4 * k + 1] = t.y; a[4 * k + 2] = t.z; a[4 * k + 3] = t.w;
         }
+        if (VEC == 4) {
+            const float2 g01 = make_float2(gv.v[0], gv.v[1]), g23 = make_float2(gv.v[VEC > 2 ? 2 : 0], gv.v[VEC > 3 ? 3 : 0]);
 #pragma unroll
-        for (int m = 0; m < MT; ++m)
+            for (int m = 0; m < MT; ++m) {
+                float2 lo = make_float2(acc[m][0], acc[m][1]), hi = make_float2(acc[m][VEC > 2 ? 2 : 0], acc[m][VEC > 3 ? 3 : 0]);
+                lo = fma2(a[m], g01, lo);
+                hi = fma2(a[m], g23, hi);
+                acc[m][0] = lo.x; acc[m][1] = lo.y; acc[m][VEC > 2 ? 2 : 0] = hi.x; acc[m][VEC > 3 ? 3 : 0] = hi.y;
+            }
+        } else {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[m][j] = fmaf(a[m], gv.v[j], acc[m][j]);
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[m][j] = fmaf(a[m], gv.v[j], acc[m][j]);
+        }
     }
 
     float *zr = z + ((size_t)b * p_out + p) * M * I + i0;
@@ -127,7 +138,7 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx_sorted, const int2 *_
 }
 
 // ------------------------------------------------------------------ K5 ------
-template <int MT, int VEC>
+template <int MT, int VEC, bool HAS_DA, bool HAS_DG>
 __global__ void __launch_bounds__(kThreads, (MT > 17 ? 1 : 2))
 coeff_grad_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
                   const float *__restrict__ dz, const float *__restrict__ x, const float *__restrict__ A,
@@ -195,67 +206,99 @@ coeff_grad_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict
 #pragma unroll
             for (int j = 0; j < VEC; ++j) d[m][j] = t.v[j];
         }
-        float *dGr = dG + (((size_t)b * p_out + p) * n_max) * I + i0;
-
+        // ---- phase A: dG[b,p,n,:] = sum_m A[p,n,m] * dz strip (coefficient row broadcast from smem) ----
+        if (HAS_DG) {
+            float *dGn = dG + (((size_t)b * p_out + p) * n_max) * I + i0;
+            const float *Arow = Av;
 #pragma unroll 2
-        for (int n = 0; n < l; ++n) {
-            const int q = iv[n];
-            const bool real = q != p_in;                // warp-uniform (same vertex)
-            Vec<VEC> gv;
-            if (active && real && dA_out != nullptr) gv.load(xb + (size_t)q * I);
-            else
+            for (int n = 0; n < l; ++n, dGn += I, Arow += MP) {
+                if (iv[n] == p_in) continue;             // warp-uniform; padding never sits below `last` in practice
+                const float4 *a4 = reinterpret_cast<const float4 *>(Arow);
+                float a[MP];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) gv.v[j] = 0.f;
-
-            // dG: A row (broadcast) x dz strip
-            const float4 *a4 = reinterpret_cast<const float4 *>(Av + n * MP);
-            float a[MP];
+                for (int k = 0; k < MP / 4; ++k) {
+                    const float4 t = a4[k];
+                    a[4 * k] = t.x; a[4 * k + 1] = t.y; a[4 * k + 2] = t.z; a[4 * k + 3] = t.w;
+                }
+                Vec<VEC> og;
+                if (VEC == 4) {
+                    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < MP / 4; ++k) {
-                const float4 t = a4[k];
-                a[4 * k] = t.x; a[4 * k + 1] = t.y; a[4 * k + 2] = t.z; a[4 * k + 3] = t.w;
+                    for (int m = 0; m < MT; ++m) {
+                        lo = fma2(a[m], make_float2(d[m][0], d[m][1]), lo);
+                        hi = fma2(a[m], make_float2(d[m][VEC > 2 ? 2 : 0], d[m][VEC > 3 ? 3 : 0]), hi);
+                    }
+                    og.v[0] = lo.x; og.v[1] = lo.y; og.v[VEC > 2 ? 2 : 0] = hi.x; og.v[VEC > 3 ? 3 : 0] = hi.y;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) og.v[j] = 0.f;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) og.v[j] = fmaf(a[m], d[m][j], og.v[j]);
+                }
+                if (active) og.store(dGn);
             }
-            Vec<VEC> og;
+        }
+        // ---- phase B: dA[p,n,m] += sum over the strip of dz * gathered x, reduced over the warp's lanes ----
+        if (HAS_DA) {
+            float *pwn = pw + lane;                      // lane m < MT owns column m of the warp-private slot
+            float *buf0 = red_w + lane, *buf1 = buf0 + MT * RS;
+            const float4 *row0 = reinterpret_cast<const float4 *>(red_w + lane * RS);
+            const float4 *row1 = reinterpret_cast<const float4 *>(red_w + MT * RS + lane * RS);
+            Vec<VEC> gnext;
+            {
+                const int q0 = l > 0 ? iv[0] : p_in;
+                if (active && q0 != p_in) gnext.load(xb + (size_t)q0 * I);
+                else
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) og.v[j] = 0.f;
+                    for (int j = 0; j < VEC; ++j) gnext.v[j] = 0.f;
+            }
+            for (int n = 0; n < l; ++n, pwn += MT) {
+                const Vec<VEC> gv = gnext;
+                {                                        // software pipeline: next neighbour's row is already in flight
+                    const int q1 = n + 1 < l ? iv[n + 1] : p_in;
+                    if (active && q1 != p_in) gnext.load(xb + (size_t)q1 * I);
+                    else
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) og.v[j] = fmaf(a[m], d[m][j], og.v[j]);
-            if (active && real && dG != nullptr) og.store(dGr + (size_t)n * I);
-
-            if (dA_out != nullptr) {                     // kernel-uniform: constant coefficients need no dA
-                // dA: per-lane partial over the strip, then a reduction over the 32 lanes of the warp.
+                        for (int j = 0; j < VEC; ++j) gnext.v[j] = 0.f;
+                }
                 if (MT == 1) {
                     float v = 0.f;
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) v = fmaf(d[0][j], gv.v[j], v);
 #pragma unroll
                     for (int s2 = 16; s2 >= 1; s2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s2);
-                    if (lane == 0) pw[n] += v;
+                    if (lane == 0) *pwn += v;
                 } else {
                     // through shared memory: lane l stores its MT partials as column l of an [MT][36] tile
                     // (conflict-free), then lane m sums row m with 8 LDS.128 (quarter-warps hit disjoint banks).
-                    // ~60 instructions per neighbour instead of ~125 for a shuffle butterfly; two buffers
-                    // alternate so one __syncwarp per neighbour is enough. Fixed order: bitwise reproducible.
-                    float *buf = red_w + (n & 1) * MT * RS;
+                    // Two buffers alternate so one __syncwarp per neighbour is enough. Fixed order: reproducible.
+                    float *buf = (n & 1) ? buf1 : buf0;
 #pragma unroll
                     for (int m = 0; m < MT; ++m) {
                         float sm = 0.f;
+                        if (VEC == 4) {
+                            float2 s2 = fma2(make_float2(d[m][0], d[m][1]), make_float2(gv.v[0], gv.v[1]), make_float2(0.f, 0.f));
+                            s2 = fma2(make_float2(d[m][VEC > 2 ? 2 : 0], d[m][VEC > 3 ? 3 : 0]),
+                                      make_float2(gv.v[VEC > 2 ? 2 : 0], gv.v[VEC > 3 ? 3 : 0]), s2);
+                            sm = s2.x + s2.y;
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) sm = fmaf(d[m][j], gv.v[j], sm);
-                        buf[m * RS + lane] = sm;
+                            for (int j = 0; j < VEC; ++j) sm = fmaf(d[m][j], gv.v[j], sm);
+                        }
+                        buf[m * RS] = sm;
                     }
                     __syncwarp();
                     if (lane < MT) {
-                        const float4 *row = reinterpret_cast<const float4 *>(buf + lane * RS);
+                        const float4 *row = (n & 1) ? row1 : row0;
                         float tot = 0.f;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float4 t4 = row[k];
                             tot += (t4.x + t4.y) + (t4.z + t4.w);
                         }
-                        pw[n * MT + lane] += tot;        // warp-private slot: no race
+                        *pwn += tot;                     // warp-private slot: no race
                     }
                 }
             }
@@ -263,7 +306,7 @@ coeff_grad_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict
     }
     __syncthreads();
 
-    if (dA_out == nullptr) return;
+    if (!HAS_DA) return;
     // cross-warp reduction in fixed warp order; padding slots get exactly 0
     const int warps_per_v = g.CB / 32;
     for (int e = tid; e < g.TP * n_max * M; e += kThreads) {
@@ -453,16 +496,23 @@ static int launch_grad(const Tables *t, const float *dz, const float *x, const f
                        float *ws, int B, int I, int M, cudaStream_t st) {
     GradPlan pl;
     if (int e = plan_grad<MT, VEC>(t, B, I, &pl)) return e;
-    auto k = coeff_grad_kernel<MT, VEC>;
-    if (int e = set_smem(k, pl.smem)) return e;
     const size_t n_dA = (size_t)t->p_out * t->n_max * M;
     if (dA != nullptr && pl.n_split > 1 && ws == nullptr)
         return fail(VCM_EINVAL, "workspace required (%d splits)", pl.n_split);
     float *target = dA == nullptr ? nullptr : (pl.n_split > 1 ? ws : dA);
     dim3 grid((unsigned)ceil_div(t->p_out, pl.g.TP), (unsigned)pl.n_split);
-    k<<<grid, kThreads, pl.smem, st>>>(t->idx_sorted, reinterpret_cast<const int2 *>(t->meta_sorted), dz, x, A, target, dG,
-                                       t->p_in, t->p_out, t->n_max,
-                                       I, M, pl.g, pl.passes, pl.n_split);
+    const int2 *meta = reinterpret_cast<const int2 *>(t->meta_sorted);
+#define VCM_K5_LAUNCH(DA_, DG_)                                                                                    \
+    do {                                                                                                           \
+        auto k = coeff_grad_kernel<MT, VEC, DA_, DG_>;                                                             \
+        if (int e = set_smem(k, pl.smem)) return e;                                                                \
+        k<<<grid, kThreads, pl.smem, st>>>(t->idx_sorted, meta, dz, x, A, target, dG, t->p_in, t->p_out, t->n_max, \
+                                           I, M, pl.g, pl.passes, pl.n_split);                                     \
+    } while (0)
+    if (dA != nullptr && dG != nullptr) VCM_K5_LAUNCH(true, true);
+    else if (dA != nullptr) VCM_K5_LAUNCH(true, false);
+    else VCM_K5_LAUNCH(false, true);
+#undef VCM_K5_LAUNCH
     VCM_LAUNCH_CHECK();
     if (dA != nullptr && pl.n_split > 1) {
         sum_splits_kernel<<<(unsigned)ceil_div((int64_t)n_dA, 256), 256, 0, st>>>(ws, dA, n_dA, pl.n_split);
