@@ -84,11 +84,13 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx_sorted, const int2 *_
     const float *Av = A_s + (size_t)v * n_max * MP;
     const int32_t *iv = idx_s + v * n_max;
 
-    float acc[MT][VEC];
+    // accumulators live as float2 pairs (aligned register pairs) so the contraction is FFMA2 with no repacking
+    constexpr int V2 = VEC == 4 ? 2 : 1;
+    float2 acc[MT][V2];
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[m][j] = 0.f;
+        for (int j = 0; j < V2; ++j) acc[m][j] = make_float2(0.f, 0.f);
 
     // No control flow in the loop body (a sentinel neighbour loads nothing and contributes an exact 0), so
     // the compiler can hoist the gathers of several neighbours ahead of the FMAs: the kernel is bound by
@@ -96,11 +98,15 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx_sorted, const int2 *_
 #pragma unroll 4
     for (int n = 0; n < l; ++n) {
         const int q = iv[n];
-        Vec<VEC> gv;
-        if (q != p_in) gv.load(xb + (size_t)q * I);
-        else
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) gv.v[j] = 0.f;
+        float2 g2[V2];
+        if (VEC == 4) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q != p_in) t4 = ldg4(xb + (size_t)q * I);
+            g2[0] = make_float2(t4.x, t4.y);
+            g2[V2 - 1] = make_float2(t4.z, t4.w);
+        } else {
+            g2[0] = make_float2(q != p_in ? __ldg(xb + (size_t)q * I) : 0.f, 0.f);
+        }
         const float4 *a4 = reinterpret_cast<const float4 *>(Av + n * MP);
         float a[MP];
 #pragma unroll
@@ -108,20 +114,14 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx_sorted, const int2 *_
             const float4 t = a4[k];
             a[4 * k] = t.x; a[4 * k + 1] = t.y; a[4 * k + 2] = t.z; a[4 * k + 3] = t.w;
         }
-        if (VEC == 4) {
-            const float2 g01 = make_float2(gv.v[0], gv.v[1]), g23 = make_float2(gv.v[VEC > 2 ? 2 : 0], gv.v[VEC > 3 ? 3 : 0]);
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                float2 lo = make_float2(acc[m][0], acc[m][1]), hi = make_float2(acc[m][VEC > 2 ? 2 : 0], acc[m][VEC > 3 ? 3 : 0]);
-                lo = fma2(a[m], g01, lo);
-                hi = fma2(a[m], g23, hi);
-                acc[m][0] = lo.x; acc[m][1] = lo.y; acc[m][VEC > 2 ? 2 : 0] = hi.x; acc[m][VEC > 3 ? 3 : 0] = hi.y;
+        for (int m = 0; m < MT; ++m) {
+            if (VEC == 4) {
+#pragma unroll
+                for (int j = 0; j < V2; ++j) acc[m][j] = fma2(a[m], g2[j], acc[m][j]);
+            } else {
+                acc[m][0].x = fmaf(a[m], g2[0].x, acc[m][0].x);
             }
-        } else {
-#pragma unroll
-            for (int m = 0; m < MT; ++m)
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) acc[m][j] = fmaf(a[m], gv.v[j], acc[m][j]);
         }
     }
 
@@ -129,10 +129,8 @@ gather_contract_fwd_kernel(const int32_t *__restrict__ idx_sorted, const int2 *_
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
         if (m < M) {
-            Vec<VEC> o;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) o.v[j] = acc[m][j];
-            o.store(zr + (size_t)m * I);
+            if (VEC == 4) st4(zr + (size_t)m * I, make_float4(acc[m][0].x, acc[m][0].y, acc[m][V2 - 1].x, acc[m][V2 - 1].y));
+            else zr[(size_t)m * I] = acc[m][0].x;
         }
     }
 }
@@ -195,16 +193,18 @@ coeff_grad_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict
         const int b = active ? c / g.IV : 0, i0 = active ? (c - b * g.IV) * VEC : 0;
         const float *xb = x + (size_t)b * p_in * I + i0;
 
-        float d[MT][VEC];
+        constexpr int V2 = VEC == 4 ? 2 : 1;
+        float2 d[MT][V2];                                // dz strip as aligned register pairs (FFMA2 operands)
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-            Vec<VEC> t;
-            if (active && m < M) t.load(dz + (((size_t)b * p_out + p) * M + m) * I + i0);
-            else
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) t.v[j] = 0.f;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) d[m][j] = t.v[j];
+            if (VEC == 4) {
+                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active && m < M) t4 = ldg4(dz + (((size_t)b * p_out + p) * M + m) * I + i0);
+                d[m][0] = make_float2(t4.x, t4.y);
+                d[m][V2 - 1] = make_float2(t4.z, t4.w);
+            } else {
+                d[m][0] = make_float2((active && m < M) ? __ldg(dz + (((size_t)b * p_out + p) * M + m) * I + i0) : 0.f, 0.f);
+            }
         }
         // ---- phase A: dG[b,p,n,:] = sum_m A[p,n,m] * dz strip (coefficient row broadcast from smem) ----
         if (HAS_DG) {
@@ -220,24 +220,20 @@ coeff_grad_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict
                     const float4 t = a4[k];
                     a[4 * k] = t.x; a[4 * k + 1] = t.y; a[4 * k + 2] = t.z; a[4 * k + 3] = t.w;
                 }
-                Vec<VEC> og;
                 if (VEC == 4) {
                     float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int m = 0; m < MT; ++m) {
-                        lo = fma2(a[m], make_float2(d[m][0], d[m][1]), lo);
-                        hi = fma2(a[m], make_float2(d[m][VEC > 2 ? 2 : 0], d[m][VEC > 3 ? 3 : 0]), hi);
+                        lo = fma2(a[m], d[m][0], lo);
+                        hi = fma2(a[m], d[m][V2 - 1], hi);
                     }
-                    og.v[0] = lo.x; og.v[1] = lo.y; og.v[VEC > 2 ? 2 : 0] = hi.x; og.v[VEC > 3 ? 3 : 0] = hi.y;
+                    if (active) st4(dGn, make_float4(lo.x, lo.y, hi.x, hi.y));
                 } else {
+                    float og = 0.f;
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) og.v[j] = 0.f;
-#pragma unroll
-                    for (int m = 0; m < MT; ++m)
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) og.v[j] = fmaf(a[m], d[m][j], og.v[j]);
+                    for (int m = 0; m < MT; ++m) og = fmaf(a[m], d[m][0].x, og);
+                    if (active) *dGn = og;
                 }
-                if (active) og.store(dGn);
             }
         }
         // ---- phase B: dA[p,n,m] += sum over the strip of dz * gathered x, reduced over the warp's lanes ----
@@ -246,27 +242,26 @@ coeff_grad_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict
             float *buf0 = red_w + lane, *buf1 = buf0 + MT * RS;
             const float4 *row0 = reinterpret_cast<const float4 *>(red_w + lane * RS);
             const float4 *row1 = reinterpret_cast<const float4 *>(red_w + MT * RS + lane * RS);
-            Vec<VEC> gnext;
-            {
-                const int q0 = l > 0 ? iv[0] : p_in;
-                if (active && q0 != p_in) gnext.load(xb + (size_t)q0 * I);
-                else
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) gnext.v[j] = 0.f;
-            }
-            for (int n = 0; n < l; ++n, pwn += MT) {
-                const Vec<VEC> gv = gnext;
-                {                                        // software pipeline: next neighbour's row is already in flight
-                    const int q1 = n + 1 < l ? iv[n + 1] : p_in;
-                    if (active && q1 != p_in) gnext.load(xb + (size_t)q1 * I);
-                    else
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) gnext.v[j] = 0.f;
+            auto gather = [&](int q, float2 (&gq)[V2]) {
+                if (VEC == 4) {
+                    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (active && q != p_in) t4 = ldg4(xb + (size_t)q * I);
+                    gq[0] = make_float2(t4.x, t4.y);
+                    gq[V2 - 1] = make_float2(t4.z, t4.w);
+                } else {
+                    gq[0] = make_float2((active && q != p_in) ? __ldg(xb + (size_t)q * I) : 0.f, 0.f);
                 }
-                if (MT == 1) {
-                    float v = 0.f;
+            };
+            float2 gnext[V2];
+            gather(l > 0 ? iv[0] : p_in, gnext);
+            for (int n = 0; n < l; ++n, pwn += MT) {
+                float2 gv[V2];
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) v = fmaf(d[0][j], gv.v[j], v);
+                for (int j = 0; j < V2; ++j) gv[j] = gnext[j];
+                gather(n + 1 < l ? iv[n + 1] : p_in, gnext);     // software pipeline: next row already in flight
+                if (MT == 1) {
+                    float v = d[0][0].x * gv[0].x;
+                    if (VEC == 4) v += d[0][0].y * gv[0].y + d[0][V2 - 1].x * gv[V2 - 1].x + d[0][V2 - 1].y * gv[V2 - 1].y;
 #pragma unroll
                     for (int s2 = 16; s2 >= 1; s2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s2);
                     if (lane == 0) *pwn += v;
@@ -277,15 +272,13 @@ coeff_grad_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict
                     float *buf = (n & 1) ? buf1 : buf0;
 #pragma unroll
                     for (int m = 0; m < MT; ++m) {
-                        float sm = 0.f;
+                        float sm;
                         if (VEC == 4) {
-                            float2 s2 = fma2(make_float2(d[m][0], d[m][1]), make_float2(gv.v[0], gv.v[1]), make_float2(0.f, 0.f));
-                            s2 = fma2(make_float2(d[m][VEC > 2 ? 2 : 0], d[m][VEC > 3 ? 3 : 0]),
-                                      make_float2(gv.v[VEC > 2 ? 2 : 0], gv.v[VEC > 3 ? 3 : 0]), s2);
+                            float2 s2 = fma2(d[m][0], gv[0], make_float2(0.f, 0.f));
+                            s2 = fma2(d[m][V2 - 1], gv[V2 - 1], s2);
                             sm = s2.x + s2.y;
                         } else {
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) sm = fmaf(d[m][j], gv.v[j], sm);
+                            sm = d[m][0].x * gv[0].x;
                         }
                         buf[m * RS] = sm;
                     }
