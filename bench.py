@@ -347,8 +347,20 @@ def roofline(trainer, resident, n_rot, steps, dump=""):
     top = max(summ, key=lambda k: summ[k]["ms"])
     v = summ[top]
     achieved = v["bytes"] / v["ms"] / 1e6                      # GB/s
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/traffic_r1.json):
+    # measured dram bytes / algorithmic bytes of the profiled launch, applied to this run's per-launch average
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        if tr["kernel"] == top:
+            traffic = tr["ratio"] * v["bytes"] / v["calls"]
+            traffic_src = "%s: %.1f MB measured vs %.1f MB algorithmic on %s" % (
+                tr["source"], tr["dram_bytes"] / 1e6, tr["algorithmic_bytes"] / 1e6, tr["layer"])
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
             "launches": v["calls"], "avg_launch_ms": v["ms"] / v["calls"],
             "algorithmic_bytes_per_launch": v["bytes"] / v["calls"],
             "how": "CUDA events around every call of this entry point on the launching stream, over %d steps "
