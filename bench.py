@@ -178,8 +178,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     dev = torch.device("cuda", local)
     # default = the north_star's design: tcgen05 TF32 basis GEMMs (fp32 storage and accumulation, stated
-    # tolerance 3e-3); the exact-fp32 CUDA-core mode (<= 1e-5 vs the reference) is timed as well and
-    # reported under "fp32_mode" so both arithmetic modes are on the same line.
+    # tolerance 3e-3); the fp32-grade mode (3-pass TF32 split on the same kernels, <= 1e-5 vs the reference) is
+    # timed as well and reported under "fp32_mode" so both arithmetic modes are on the same line.
     precision = args.precision
     if precision == "auto":
         precision = os.environ.get("VCM_DEFAULT_PRECISION", "tf32")
@@ -261,16 +261,20 @@ def run_ours(args):
     value = gbatch * args.steps / (ms / 1e3)
     e2e = gbatch * args.steps / (ms_e2e / 1e3)
 
+    # fp32-grade arithmetic (<= 1e-5 vs the reference) on the same tensor-core kernels: 3-pass TF32 hi/lo split.
+    # Re-captured as its own CUDA graph and timed the same way.
     fp32_mode = None
-    if precision != "fp32" and not args.no_fp32_mode:
-        F_.set_precision("fp32")
+    if precision == "tf32" and not args.no_fp32_mode:
+        F_.set_precision("tf32x3")
         g, trainer._graph = trainer._graph, None
-        n32 = max(3, min(args.steps, 8))
+        if not args.no_graph:
+            trainer.capture(resident[0][0], resident[0][1], warmup=2)
         for i in range(3):
             step_resident(i)
-        ms32, _, _, _ = timed(step_resident, n32)
-        fp32_mode = {"value": gbatch * n32 / (ms32 / 1e3), "unit": "meshes/s", "ms_per_step": ms32 / n32,
-                     "steps": n32, "launch": "eager", "gemm": "fp32 FMA on CUDA cores (<= 1e-5 vs reference)"}
+        ms32, _, _, _ = timed(step_resident, args.steps)
+        fp32_mode = {"value": gbatch * args.steps / (ms32 / 1e3), "unit": "meshes/s", "ms_per_step": ms32 / args.steps,
+                     "steps": args.steps, "gemm_precision": "tf32x3",
+                     "gemm": "tcgen05, 3-pass TF32 hi/lo split: fp32-grade (<= 1e-5 vs reference, tests/test_gpu_gemm_tc.py)"}
         trainer._graph = g
         F_.set_precision(precision)
 

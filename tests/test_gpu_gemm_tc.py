@@ -196,3 +196,69 @@ def test_gather_contract_on_tensor_pipe(cfg):
     assert not torch.isnan(z_tc).any()
     assert rel_err(z_tc.cpu().numpy(), want.cpu().numpy()) < EXACT_TOL
     assert rel_err(z_tc.cpu().numpy(), z_32.cpu().numpy()) < TF32_TOL
+
+
+X3 = _lib.PRECISIONS["tf32x3"]
+X3_TOL = 1e-5        # the fp32 bar of the north_star, met on tensor cores by the 3-pass hi/lo split
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "R%d_M%d_I%d_O%d" % s)
+def test_tf32x3_gemms_are_fp32_grade(shape):
+    R, M, I, O = shape
+    L = _lib.lib()
+    if not L.vcm_basis_uses_tensor_cores(R, M, I, O, X3):
+        pytest.skip("no tensor-core kernel for this shape")
+    z, W, ds = _case(R, M, I, O, 7)
+    Wk = W.view(M, O, I).permute(0, 2, 1).reshape(M * I, O).double()
+    st = _lib.stream_ptr()
+    out = torch.full((R, O), float("nan"), device="cuda")
+    ws = torch.empty(max(L.vcm_basis_fwd_workspace(R, M, I, O, X3), L.vcm_basis_bwd_dz_workspace(R, M, I, O, X3),
+                         L.vcm_basis_bwd_dw_workspace(R, M, I, O, X3), 1), device="cuda")
+    _lib.check(L.vcm_basis_fwd(z.data_ptr(), W.data_ptr(), None, 0, None, None, out.data_ptr(), ws.data_ptr(), 1, R, M, I,
+                               O, 0, 1.0, 0.0, X3, st))
+    assert rel_err(out.cpu().numpy(), (z.double() @ Wk).cpu().numpy()) < X3_TOL
+    dz = torch.full((R, M * I), float("nan"), device="cuda")
+    _lib.check(L.vcm_basis_bwd_dz(ds.data_ptr(), W.data_ptr(), dz.data_ptr(), ws.data_ptr(), R, M, I, O, 0, X3, st))
+    assert rel_err(dz.cpu().numpy(), (ds.double() @ Wk.t()).cpu().numpy()) < X3_TOL
+    dW = torch.full((M, O * I), float("nan"), device="cuda")
+    _lib.check(L.vcm_basis_bwd_dw(ds.data_ptr(), z.data_ptr(), dW.data_ptr(), ws.data_ptr(), R, M, I, O, X3, st))
+    want = (z.double().t() @ ds.double()).view(M, I, O).permute(0, 2, 1).reshape(M, O * I)
+    assert rel_err(dW.cpu().numpy(), want.cpu().numpy()) < X3_TOL
+
+
+def test_layer_in_tf32x3_mode_meets_the_fp32_bar():
+    from oracle import vcconv_oracle as orc
+    from vcmeshconv_b200 import functional as F_
+    from vcmeshconv_b200 import graph_sampling as gs
+    from vcmeshconv_b200 import graphVAESSW as vae
+    from vcmeshconv_b200 import synthetic
+    pts, faces = synthetic.sphere(1500, seed=1)
+    tabs, nums = gs.build_tables(faces, 1500, [(1, 1, 1), (2, 2, 2)])
+    table, p_in, cin, cout, m = tabs["unpool1"], nums[2], 64, 32, 17
+    gen = torch.Generator().manual_seed(3)
+    layer_o = orc.Layer(table, cin, cout, p_in, 0.9)
+    params = orc.init_layer_params(table, cin, cout, m, p_in, True, 0.9, gen, torch.float64)
+    coeffs = orc.init_coeffs(table, m, gen, torch.float64) * 4
+    x = torch.randn(3, p_in, cin, generator=gen, dtype=torch.float64) * 0.3
+    gy = torch.randn(3, table.shape[0], cout, generator=gen, dtype=torch.float64)
+    for t in [x, coeffs] + list(params.values()):
+        t.requires_grad_(True)
+    y_ref = layer_o(x, coeffs, params)
+    y_ref.backward(gy)
+    layer = vae.LASMConvssw(cin, cout, m, p_in, table, True, 0.9)
+    layer.load_state_dict({**{k: v.detach().float() for k, v in params.items()},
+                           "neighbor_num_lst": layer.neighbor_num_lst, "neighbor_id_lstlst": layer.neighbor_id_lstlst})
+    layer = layer.cuda()
+    prev = F_.set_precision("tf32x3")
+    try:
+        xg = x.detach().float().cuda().requires_grad_(True)
+        Ag = coeffs.detach().float().cuda().requires_grad_(True)
+        y = layer(xg, Ag)
+        y.backward(gy.float().cuda())
+    finally:
+        F_.set_precision(prev)
+    assert rel_err(y.detach().cpu().numpy(), y_ref.detach().numpy()) < X3_TOL
+    assert rel_err(xg.grad.cpu().numpy(), x.grad.numpy()) < X3_TOL
+    assert rel_err(Ag.grad.cpu().numpy(), coeffs.grad.numpy()) < X3_TOL
+    for k, p in layer.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), params[k].grad.numpy()) < X3_TOL, k

@@ -32,7 +32,17 @@ def _module_from_golden(g):
 
 def test_library_is_the_cuda_one():
     assert _lib.lib().vcm_version() >= 100
-    assert F_.get_precision() == "fp32"
+    assert F_.get_precision() == "tf32x3"          # default: fp32-grade on tensor cores; meets the 1e-5 bar below
+
+
+@pytest.mark.parametrize("case", ["layer_pool_plain", "layer_conv_res_same", "layer_tets_pool_res"])
+def test_layer_in_cuda_core_fp32_mode(case):
+    """Same golden comparison with the GEMMs forced onto the fp32 CUDA-core kernels."""
+    prev = F_.set_precision("fp32")
+    try:
+        test_layer_forward_backward_vs_reference_gold(case)
+    finally:
+        F_.set_precision(prev)
 
 
 @pytest.mark.parametrize("case", layer_cases())

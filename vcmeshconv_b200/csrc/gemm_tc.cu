@@ -190,12 +190,18 @@ __device__ __forceinline__ float elu1(float t) { return t > 0.f ? t : expm1f(t);
 // RT: 128-row tiles per CTA sharing one B tile (RT = 2: a 256 x BN output tile in two TMEM accumulators).
 // The dz GEMM is bound by operand re-reads from L2 (its reduction is short, its output huge); two row
 // tiles per B tile cut that traffic by a third.
-template <int BN, int MODE, int STAGES, int RT>
+// X3: fp32-grade arithmetic on the tensor cores. The MMA reads only the top 19 bits of an fp32 operand (TF32), so
+// every operand tile is split in shared memory into hi = the tile as loaded (the hardware truncates it) and
+// lo = x - trunc_tf32(x) (exact in fp32), and each k-step issues hi*hi + lo*hi + hi*lo: the dropped lo*lo term and
+// the truncation of lo are ~2^-22 relative. The split is elementwise, hence layout-agnostic (works on the swizzled
+// tiles as they are); the four epilogue warps, idle during the main loop, do it between TMA arrival and MMA issue.
+template <int BN, int MODE, int STAGES, int RT, bool X3>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const TcParams p) {
     constexpr int B_BYTES = BN * TK * 4;
-    constexpr int STAGE_BYTES = RT * A_BYTES + B_BYTES;
+    constexpr int HI_BYTES = RT * A_BYTES + B_BYTES;            // what TMA fills per stage
+    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * HI_BYTES;        // + the lo copies
     static_assert(RT == 1 || MODE != MODE_DW, "row-tile pairing is for the row-major GEMMs");
     static_assert(RT * BN <= 512, "TMEM has 512 columns");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -204,7 +210,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *empty = full + STAGES;
     uint64_t *acc_full = empty + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    uint64_t *split_done = acc_full + 1;                         // [STAGES], X3 only
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(split_done + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, n_tile = blockIdx.y, split = blockIdx.z;
@@ -216,6 +223,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&split_done[s], 128);
         }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -236,7 +244,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
             mbar_wait(&empty[s], ph ^ 1u);
-            mbar_expect_tx(&full[s], STAGE_BYTES);
+            mbar_expect_tx(&full[s], HI_BYTES);
             const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + RT * A_BYTES;
             const int kb = kb_begin + it;
             if (MODE == MODE_DW) {
@@ -260,7 +268,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int it = 0; it < n_iter; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            mbar_wait(&full[s], ph);
+            mbar_wait(X3 ? &split_done[s] : &full[s], ph);
             tc_fence_after();
             const uint32_t a_base = smem_base + s * STAGE_BYTES, b_base = a_base + RT * A_BYTES;
 #pragma unroll
@@ -279,6 +287,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     db = make_desc(b_base + j * 32, 16, 1024);
                 }
                 umma_tf32(tmem_base + (uint32_t)(t * BN), da, db, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                if (X3) {
+                    // the lo tiles sit HI_BYTES further (descriptor address field is in 16-byte units)
+                    const uint64_t lo_off = (uint64_t)(HI_BYTES >> 4);
+                    umma_tf32(tmem_base + (uint32_t)(t * BN), da + lo_off, db, idesc, 1u);
+                    umma_tf32(tmem_base + (uint32_t)(t * BN), da, db + lo_off, idesc, 1u);
+                }
             }
             umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
         }
@@ -287,6 +301,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== epilogue =====
         const int q = warp - 4;                // TMEM lane quarter of this warp
         const int row = q * 32 + lane;         // accumulator row owned by this thread
+        if (X3) {
+            // ===== operand splitter (main loop) =====
+            const int t128 = threadIdx.x - 128;
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(&full[s], ph);                           // TMA bytes have landed
+                float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * STAGE_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * STAGE_BYTES + HI_BYTES);
+#pragma unroll 4
+                for (int e = t128; e < HI_BYTES / 16; e += 128) {
+                    const float4 v = hi[e];
+                    float4 r;
+                    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    lo[e] = r;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> MMA (async proxy)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_done[s])) : "memory");
+            }
+        }
         mbar_wait(acc_full, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -473,31 +510,37 @@ int pick_bn(int n) {       // n % 32 == 0
     return 32;
 }
 
-template <int MODE, int STAGES, int RT = 1>
-int launch(int bn, dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, const TcParams &p,
-           cudaStream_t st) {
-#define VCM_TC_CASE(BN_)                                                                                          \
-    case BN_: {                                                                                                   \
-        auto k = tc_gemm_kernel<BN_, MODE, STAGES, RT>;                                                           \
-        const int smem = STAGES * (RT * A_BYTES + BN_ * TK * 4) + 1024 + 256;                                     \
-        VCM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
-        k<<<grid, NTHREADS, smem, st>>>(ma, mb, mc, p);                                                           \
-        break;                                                                                                    \
-    }
-    switch (bn) {
-        VCM_TC_CASE(32)
-        VCM_TC_CASE(64)
-        VCM_TC_CASE(128)
-        VCM_TC_CASE(256)
-        default: return fail(VCM_EUNSUPPORTED, "no tensor-core tile of width %d", bn);
-    }
-#undef VCM_TC_CASE
+constexpr int stages_for(int mode, int bn, bool x3) {
+    // dz: short reduction, big output -> 2 stages (two CTAs per SM when they fit); K2 / K4: as deep as fits in 227 KB
+    if (mode == MODE_DZ) return 2;
+    if (!x3) return 4;
+    return bn >= 256 ? 2 : (bn >= 128 ? 3 : 4);
+}
+
+template <int MODE, int BN_, bool X3>
+int launch_one(dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, const TcParams &p,
+               cudaStream_t st) {
+    constexpr int ST = stages_for(MODE, BN_, X3);
+    auto k = tc_gemm_kernel<BN_, MODE, ST, 1, X3>;
+    const int smem = ST * (X3 ? 2 : 1) * (A_BYTES + BN_ * TK * 4) + 1024 + 512;
+    VCM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<grid, NTHREADS, smem, st>>>(ma, mb, mc, p);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
 
-// Split count that wastes the least machine time to wave quantisation: CTAs = tiles * split run in
-// ceil(CTAs / slots) waves of `slots` concurrent CTAs; every CTA works through num_kb / split k-blocks.
+template <int MODE>
+int launch(int bn, bool x3, dim3 grid, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc,
+           const TcParams &p, cudaStream_t st) {
+    switch (bn) {
+        case 32: return x3 ? launch_one<MODE, 32, true>(grid, ma, mb, mc, p, st) : launch_one<MODE, 32, false>(grid, ma, mb, mc, p, st);
+        case 64: return x3 ? launch_one<MODE, 64, true>(grid, ma, mb, mc, p, st) : launch_one<MODE, 64, false>(grid, ma, mb, mc, p, st);
+        case 128: return x3 ? launch_one<MODE, 128, true>(grid, ma, mb, mc, p, st) : launch_one<MODE, 128, false>(grid, ma, mb, mc, p, st);
+        case 256: return x3 ? launch_one<MODE, 256, true>(grid, ma, mb, mc, p, st) : launch_one<MODE, 256, false>(grid, ma, mb, mc, p, st);
+    }
+    return fail(VCM_EUNSUPPORTED, "no tensor-core tile of width %d", bn);
+}
+
 int tune_flag(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -542,7 +585,7 @@ DwSplit plan_dw_tc(int64_t R, int K, int O) {
 }  // namespace
 
 bool tc_supported(int which, int64_t R, int M, int I, int O, int precision) {
-    if (precision != VCM_PREC_TF32) return false;           // TF32X3 not built yet: stays on fp32 CUDA cores
+    if (precision != VCM_PREC_TF32 && precision != VCM_PREC_TF32X3) return false;
     // bring-up switch: VCM_TC_DISABLE is a bit mask (1 fwd, 2 dz, 4 dW) of GEMMs kept on the CUDA-core kernels
     static const int disabled = [] { const char *e = getenv("VCM_TC_DISABLE"); return e ? atoi(e) : 0; }();
     if (disabled & (1 << which)) return false;
@@ -576,7 +619,6 @@ size_t tc_basis_fwd_workspace(int64_t R, int M, int I, int O) {
 int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_point, const float *res, float *y_act,
                  float *out, float *ws, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr,
                  int precision, cudaStream_t st) {
-    (void)precision;
     const int K = M * I, bn = pick_bn(O);
     CUtensorMap ma, mb;
     {
@@ -599,7 +641,7 @@ int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_poin
     p.bias = bias; p.res = res; p.y_act = y_act; p.out = out; p.per_point = per_point; p.act = act; p.sy = sy; p.sr = sr;
     p.partial = n_split > 1 ? ws : nullptr;
     dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(O, bn), (unsigned)n_split);
-    if (int e = launch<MODE_FWD, 4>(bn, grid, ma, mb, ma, p, st)) return e;
+    if (int e = launch<MODE_FWD>(bn, precision == VCM_PREC_TF32X3, grid, ma, mb, ma, p, st)) return e;
     if (n_split > 1) {
         splitk_fwd_epilogue_kernel<<<(unsigned)ceil_div(R * O / 4, 256), 256, 0, st>>>(ws, n_split, R, O, P_out, bias,
                                                                                       per_point, res, y_act, out, act,
@@ -613,7 +655,6 @@ size_t tc_basis_bwd_dz_workspace(int M, int I, int O) { return (size_t)M * I * O
 
 int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64_t R, int M, int I, int O,
                     int accumulate, int precision, cudaStream_t st) {
-    (void)precision;
     if (accumulate) return fail(VCM_EUNSUPPORTED, "tensor-core dz does not accumulate");
     const int K = M * I, bn = pick_bn(K);
     // stacked bases Wt[K][O]
@@ -641,25 +682,17 @@ int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64
         const uint32_t b[2] = {TK, TM};
         if (int e = make_map(&mc, dz, 2, d, s2, b)) return e;
     }
-    // enough tiles to fill the machine twice: pair row tiles (256 x BN per CTA, one B tile for both)
-    static const bool pair = [] { const char *e = getenv("VCM_DZ_PAIR"); return e && atoi(e) != 0; }();
-    if (pair && ceil_div(R, 2 * TM) * ceil_div(K, bn) >= 2 * (int64_t)sm_count()) {
-        dim3 grid2((unsigned)ceil_div(R, 2 * TM), (unsigned)ceil_div(K, bn), 1);
-        return launch<MODE_DZ, 2, 2>(bn, grid2, ma, mb, mc, p, st);
-    }
     dim3 grid((unsigned)ceil_div(R, TM), (unsigned)ceil_div(K, bn), 1);
-    return launch<MODE_DZ, 2>(bn, grid, ma, mb, mc, p, st);
+    return launch<MODE_DZ>(bn, precision == VCM_PREC_TF32X3, grid, ma, mb, mc, p, st);
 }
 
 size_t tc_basis_bwd_dw_workspace(int64_t R, int M, int I, int O, int precision) {
-    (void)precision;
     const DwSplit s = plan_dw_tc(R, M * I, O);
     return (size_t)s.n_split * M * I * O;
 }
 
 int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64_t R, int M, int I, int O,
                     int precision, cudaStream_t st) {
-    (void)precision;
     const int K = M * I, bn = pick_bn(O);
     const DwSplit sp = plan_dw_tc(R, K, O);
     CUtensorMap ma, mb;
@@ -679,7 +712,7 @@ int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64
     p.direct = sp.n_split == 1;
     p.out = p.direct ? dW : ws;
     dim3 grid((unsigned)ceil_div(K, TM), (unsigned)ceil_div(O, bn), (unsigned)sp.n_split);
-    if (int e = launch<MODE_DW, 4>(bn, grid, ma, mb, ma, p, st)) return e;
+    if (int e = launch<MODE_DW>(bn, precision == VCM_PREC_TF32X3, grid, ma, mb, ma, p, st)) return e;
     if (p.direct) return VCM_OK;
     const size_t n = (size_t)K * O;
     sum_partials_kernel<<<(unsigned)ceil_div((int64_t)(n / 4), 256), 256, 0, st>>>(ws, dW, n, sp.n_split);

@@ -17,12 +17,15 @@ import torch
 
 from . import _lib
 
-_precision = _lib.PREC_FP32
+# Default: fp32-grade results on the tensor cores (3-pass TF32 hi/lo split, <= 1e-5 vs the reference; shapes the
+# tcgen05 kernels do not take run the fp32 CUDA-core kernels). 'tf32' is the fast mode (stated tolerance 3e-3),
+# 'fp32' forces CUDA-core FMA everywhere.
+_precision = _lib.PRECISIONS[__import__("os").environ.get("VCM_PRECISION", "tf32x3")]
 
 
 def set_precision(name):
-    """'fp32' (CUDA-core FMA, the reference's arithmetic), 'tf32' or 'tf32x3'
-    (tcgen05 tensor cores; see include/vcmesh.h). Returns the previous mode."""
+    """'tf32x3' (default: tcgen05 with hi/lo split, fp32-grade), 'tf32' (tcgen05, single pass) or 'fp32'
+    (CUDA-core FMA, the reference's own arithmetic); see include/vcmesh.h. Returns the previous mode."""
     global _precision
     prev = {v: k for k, v in _lib.PRECISIONS.items()}[_precision]
     _precision = _lib.PRECISIONS[name]
