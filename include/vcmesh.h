@@ -139,6 +139,13 @@ VCM_API size_t vcm_coeff_grad_workspace(const vcm_tables *t, int B, int I, int M
 VCM_API int vcm_coeff_grad(const vcm_tables *t, const float *dz, const float *x, const float *A, float *dA,
                            float *dG, float *workspace, int B, int I, int M, void *stream);
 
+/* Same gradients with the arithmetic mode of the basis GEMMs: in VCM_PREC_TF32 / VCM_PREC_TF32X3 both are small
+ * per-vertex GEMMs on the tensor pipe (mma.sync m16n8k8 tf32; TF32X3 = hi/lo split, fp32-grade) when M <= 24,
+ * I % 16 == 0 and N <= 64; every other case is the fp32 kernel above. Use the matching workspace query. */
+VCM_API size_t vcm_coeff_grad_workspace_ex(const vcm_tables *t, int B, int I, int M, int precision);
+VCM_API int vcm_coeff_grad_ex(const vcm_tables *t, const float *dz, const float *x, const float *A, float *dA,
+                              float *dG, float *workspace, int B, int I, int M, int precision, void *stream);
+
 /* dX by the reverse (CSR-transposed) neighbour list (K6), no atomics:
  *   dx[b,q,i] = sum_{slot in rev(q)} dG[b, slot, i]  (+ dx[b,q,i] if accumulate)
  * Replaces the index_add_ scatter autograd runs for graphVAESSW.py:122. */

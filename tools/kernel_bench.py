@@ -47,7 +47,7 @@ def main():
     ds = torch.randn(B, P, O, device="cuda")
     out = torch.empty(B, P, O, device="cuda")
     dW = torch.empty_like(W)
-    ws = torch.empty(max(L.vcm_coeff_grad_workspace(t.handle, B, I, M), L.vcm_basis_bwd_dw_workspace(B * P, M, I, O, prec),
+    ws = torch.empty(max(L.vcm_coeff_grad_workspace_ex(t.handle, B, I, M, prec), L.vcm_basis_bwd_dw_workspace(B * P, M, I, O, prec),
                          L.vcm_basis_bwd_dz_workspace(B * P, M, I, O, prec), L.vcm_basis_fwd_workspace(B * P, M, I, O, prec), 1),
                      device="cuda")
     nnz = t.nnz
@@ -55,8 +55,8 @@ def main():
     calls = {
         "k1": (lambda: L.vcm_gather_contract_fwd_ex(t.handle, x.data_ptr(), A.data_ptr(), z.data_ptr(), B, I, M, prec, st),
                X + Ab + 4 * nnz + Z, 2 * B * nnz * M * I),
-        "k5": (lambda: L.vcm_coeff_grad(t.handle, dz.data_ptr(), x.data_ptr(), A.data_ptr(), dA.data_ptr(), dG.data_ptr(),
-                                        ws.data_ptr(), B, I, M, st), Z + X + 2 * Ab + 4 * nnz + Gb, 4 * B * nnz * M * I),
+        "k5": (lambda: L.vcm_coeff_grad_ex(t.handle, dz.data_ptr(), x.data_ptr(), A.data_ptr(), dA.data_ptr(), dG.data_ptr(),
+                                           ws.data_ptr(), B, I, M, prec, st), Z + X + 2 * Ab + 4 * nnz + Gb, 4 * B * nnz * M * I),
         "k6": (lambda: L.vcm_scatter_rev(t.handle, dG.data_ptr(), dx.data_ptr(), B, I, 0, st), Gb + 4 * nnz + X, B * nnz * I),
         "fwd": (lambda: L.vcm_basis_fwd(z.data_ptr(), W.data_ptr(), None, 0, None, None, out.data_ptr(), ws.data_ptr(), B, P,
                                         M, I, O, 1, 1.0, 0.0, prec, st), Z + Wb + Y, 2 * B * P * M * I * O),

@@ -952,3 +952,266 @@ extern "C" int vcm_gather_contract_fwd_ex(const vcm_tables *h, const float *x, c
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
+
+// ---------------------------------------------------------------------------
+// K5 on the tensor pipe. Per output vertex both gradients are small GEMMs over the vertex's columns c = (b, i):
+//   dG[c, n] = sum_m dz[c, m] * A_p[n, m]          (M = columns, N = neighbours, K = bases)
+//   dA[n, m] = sum_c G[n, c]  * dz[c, m]           (M = neighbours, N = bases, K = columns)
+// With 17 bases and a few dozen neighbours per vertex (and a different A_p per vertex) these are far below
+// tcgen05's 128-row tiles; warp-level mma.sync m16n8k8 (tf32 operands, fp32 accumulate) fits them exactly. The
+// fp32 kernel above is issue-bound (~345 instructions per neighbour and 128 columns, 2/3 of them not FMAs: the
+// 17-row lane reduction of dA and integer addressing); here dA accumulates in MMA fragments across ALL column
+// tiles of a warp - no per-neighbour reduction at all - and dG is 3 HMMA per 8 neighbours.
+// X3 = fp32-grade: every operand is split into hi (what the tensor core reads) and lo = x - trunc_tf32(x), and
+// each product is hi*hi + lo*hi + hi*lo (coefficients are pre-split when staged in shared memory).
+namespace vcm {
+
+constexpr int kK5S = 36;           // smem row stride of the coefficient tiles: (g*36 + t) mod 32 is a permutation
+
+__device__ __forceinline__ uint32_t tf32_lo(uint32_t a) {
+    return __float_as_uint(__uint_as_float(a) - __uint_as_float(a & 0xFFFFE000u));
+}
+
+template <bool X3>
+__device__ __forceinline__ void mma_x(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&al)[4], uint32_t b0,
+                                      uint32_t b1, uint32_t bl0, uint32_t bl1) {
+    mma_tf32_16x8x8(d, a[0], a[1], a[2], a[3], b0, b1);
+    if (X3) {
+        mma_tf32_16x8x8(d, al[0], al[1], al[2], al[3], b0, b1);
+        mma_tf32_16x8x8(d, a[0], a[1], a[2], a[3], bl0, bl1);
+    }
+}
+
+template <int NT16, bool X3, bool HAS_DA, bool HAS_DG>
+__global__ void __launch_bounds__(128, NT16 <= 2 ? 4 : 3)
+coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
+                      const float *__restrict__ dz, const float *__restrict__ x, const float *__restrict__ A,
+                      float *__restrict__ dA_out, float *__restrict__ dG, int p_in, int p_out, int n_max, int I, int M,
+                      int B, int tiles_per_cta) {
+    constexpr int NP = NT16 * 16;                                    // padded neighbour count
+    extern __shared__ __align__(16) float smem[];
+    float *A_s = smem;                                               // [NP][kK5S]  coefficients (hi = as is)
+    float *Al_s = A_s + NP * kK5S;                                   // [NP][kK5S]  lo parts (X3)
+    int32_t *idx_s = reinterpret_cast<int32_t *>(Al_s + NP * kK5S);  // [NP], -1 = no neighbour
+    float *part_s = reinterpret_cast<float *>(idx_s + NP);           // [4 warps][NP][24] (reuses nothing: small)
+
+    const int slot = blockIdx.x;
+    const int2 meta = __ldg(meta_sorted + slot);
+    const int p = meta.x, l = meta.y;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NP * kK5S; e += 128) {
+        const int n = e / kK5S, m = e - n * kK5S;
+        const float a = (n < l && m < M) ? __ldg(A + ((size_t)p * n_max + n) * M + m) : 0.f;
+        A_s[e] = a;
+        Al_s[e] = __uint_as_float(tf32_lo(__float_as_uint(a)));
+    }
+    for (int n = tid; n < NP; n += 128) {
+        const int q = n < l ? __ldg(idx_sorted + (size_t)slot * n_max + n) : p_in;
+        idx_s[n] = q == p_in ? -1 : q;
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int tiles_per_b = I >> 4, n_tiles = B * tiles_per_b;
+    const int tile_end = min(n_tiles, (int)(blockIdx.y + 1) * tiles_per_cta);
+    float acc[NT16][3][4];
+#pragma unroll
+    for (int a = 0; a < NT16; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 3; ++b2) acc[a][b2][0] = acc[a][b2][1] = acc[a][b2][2] = acc[a][b2][3] = 0.f;
+
+    for (int ct = blockIdx.y * tiles_per_cta + warp; ct < tile_end; ct += 4) {
+        const int b = ct / tiles_per_b, i0 = (ct - b * tiles_per_b) << 4;
+        const float *dzp = dz + (((size_t)b * p_out + p) * M) * I + i0;        // [m][16 columns], row stride I
+        if (HAS_DG) {
+            // dz as the A operand (row = column c, col = basis m), three k-steps of 8 bases
+            uint32_t zA[3][4], zAl[3][4];
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                const int m_lo = ks * 8 + t, m_hi = m_lo + 4;
+                zA[ks][0] = m_lo < M ? __float_as_uint(__ldg(dzp + (size_t)m_lo * I + g)) : 0u;
+                zA[ks][1] = m_lo < M ? __float_as_uint(__ldg(dzp + (size_t)m_lo * I + g + 8)) : 0u;
+                zA[ks][2] = m_hi < M ? __float_as_uint(__ldg(dzp + (size_t)m_hi * I + g)) : 0u;
+                zA[ks][3] = m_hi < M ? __float_as_uint(__ldg(dzp + (size_t)m_hi * I + g + 8)) : 0u;
+                if (X3) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) zAl[ks][r] = tf32_lo(zA[ks][r]);
+                }
+            }
+            float *dGp = dG + (((size_t)b * p_out + p) * n_max) * I + i0 + g;
+#pragma unroll
+            for (int nt = 0; nt < 2 * NT16; ++nt) {
+                if (nt * 8 >= l) break;                                        // warp-uniform
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                const float *Ar = A_s + (nt * 8 + g) * kK5S + t, *Alr = Al_s + (nt * 8 + g) * kK5S + t;
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks)
+                    mma_x<X3>(d, zA[ks], zAl[ks], __float_as_uint(Ar[ks * 8]), __float_as_uint(Ar[ks * 8 + 4]),
+                              __float_as_uint(Alr[ks * 8]), __float_as_uint(Alr[ks * 8 + 4]));
+                const int n0 = nt * 8 + 2 * t;
+                if (n0 < l && idx_s[n0] >= 0) {
+                    dGp[(size_t)n0 * I] = d[0];
+                    dGp[(size_t)n0 * I + 8] = d[2];
+                }
+                if (n0 + 1 < l && idx_s[n0 + 1] >= 0) {
+                    dGp[(size_t)(n0 + 1) * I] = d[1];
+                    dGp[(size_t)(n0 + 1) * I + 8] = d[3];
+                }
+            }
+        }
+        if (HAS_DA) {
+            const float *xb = x + (size_t)b * p_in * I + i0 + t;
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {                                   // two k-steps of 8 columns
+                // dz as the B operand (k = column, n = basis)
+                uint32_t zB[3][2], zBl[3][2];
+#pragma unroll
+                for (int mt = 0; mt < 3; ++mt) {
+                    const int m = mt * 8 + g;
+                    zB[mt][0] = m < M ? __float_as_uint(__ldg(dzp + (size_t)m * I + kc * 8 + t)) : 0u;
+                    zB[mt][1] = m < M ? __float_as_uint(__ldg(dzp + (size_t)m * I + kc * 8 + t + 4)) : 0u;
+                    if (X3) {
+                        zBl[mt][0] = tf32_lo(zB[mt][0]);
+                        zBl[mt][1] = tf32_lo(zB[mt][1]);
+                    }
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT16; ++nt) {
+                    if (nt * 16 >= l) break;                                   // warp-uniform
+                    const int q_lo = idx_s[nt * 16 + g], q_hi = idx_s[nt * 16 + g + 8];
+                    uint32_t xa[4] = {0u, 0u, 0u, 0u}, xal[4] = {0u, 0u, 0u, 0u};
+                    if (q_lo >= 0) {
+                        const float *r = xb + (size_t)q_lo * I + kc * 8;
+                        xa[0] = __float_as_uint(__ldg(r));
+                        xa[2] = __float_as_uint(__ldg(r + 4));
+                    }
+                    if (q_hi >= 0) {
+                        const float *r = xb + (size_t)q_hi * I + kc * 8;
+                        xa[1] = __float_as_uint(__ldg(r));
+                        xa[3] = __float_as_uint(__ldg(r + 4));
+                    }
+                    if (X3) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) xal[r] = tf32_lo(xa[r]);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 3; ++mt)
+                        mma_x<X3>(acc[nt][mt], xa, xal, zB[mt][0], zB[mt][1], zBl[mt][0], zBl[mt][1]);
+                }
+            }
+        }
+    }
+    if (!HAS_DA) return;
+
+    // fragments -> smem, then a fixed-order sum over the four warps; padding slots get exactly 0
+    float *pw = part_s + (size_t)warp * NP * 24;
+#pragma unroll
+    for (int nt = 0; nt < NT16; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {
+            const int n = nt * 16 + g, m = mt * 8 + 2 * t;
+            pw[n * 24 + m] = acc[nt][mt][0];
+            pw[n * 24 + m + 1] = acc[nt][mt][1];
+            pw[(n + 8) * 24 + m] = acc[nt][mt][2];
+            pw[(n + 8) * 24 + m + 1] = acc[nt][mt][3];
+        }
+    __syncthreads();
+    float *dst = dA_out + ((size_t)blockIdx.y * p_out + p) * n_max * M;
+    for (int e = tid; e < n_max * M; e += 128) {
+        const int n = e / M, m = e - n * M;
+        float s = 0.f;
+        if (n < l && idx_s[n] >= 0)
+            s = (part_s[n * 24 + m] + part_s[(NP + n) * 24 + m]) + (part_s[(2 * NP + n) * 24 + m] + part_s[(3 * NP + n) * 24 + m]);
+        dst[e] = s;
+    }
+}
+
+struct MmaGradPlan { int nt16, gy, tiles_per_cta; size_t smem; };
+
+static bool plan_grad_mma(const Tables *t, int B, int I, int M, MmaGradPlan *pl) {
+    if (M > 24 || M < 2 || (I & 15) != 0 || t->n_max > 64 || t->p_out == 0) return false;
+    pl->nt16 = (t->n_max + 15) / 16;
+    const int n_tiles = B * (I >> 4);
+    int64_t want = ceil_div(8 * (int64_t)sm_count(), t->p_out);        // ~8 CTAs of 4 warps per SM overall
+    if (want < 1) want = 1;
+    const int64_t max_gy = ceil_div(n_tiles, 8);                       // at least two tiles per warp
+    int64_t gy = want < max_gy ? want : max_gy;
+    if (gy < 1) gy = 1;
+    pl->tiles_per_cta = (int)(ceil_div(ceil_div(n_tiles, gy), 4) * 4);
+    pl->gy = (int)ceil_div(n_tiles, pl->tiles_per_cta);
+    const int NP = pl->nt16 * 16;
+    pl->smem = ((size_t)2 * NP * kK5S + NP + (size_t)4 * NP * 24) * sizeof(float);
+    return true;
+}
+
+template <int NT16, bool X3>
+static int launch_grad_mma(const Tables *t, const MmaGradPlan &pl, const float *dz, const float *x, const float *A,
+                           float *target, float *dG, int B, int I, int M, cudaStream_t st) {
+    dim3 grid((unsigned)t->p_out, (unsigned)pl.gy);
+    const int2 *meta = reinterpret_cast<const int2 *>(t->meta_sorted);
+#define VCM_K5M(DA_, DG_)                                                                                           \
+    do {                                                                                                            \
+        auto k = coeff_grad_mma_kernel<NT16, X3, DA_, DG_>;                                                         \
+        if (int e = set_smem(k, pl.smem)) return e;                                                                 \
+        k<<<grid, 128, pl.smem, st>>>(t->idx_sorted, meta, dz, x, A, target, dG, t->p_in, t->p_out, t->n_max, I, M, \
+                                      B, pl.tiles_per_cta);                                                         \
+    } while (0)
+    if (target != nullptr && dG != nullptr) VCM_K5M(true, true);
+    else if (target != nullptr) VCM_K5M(true, false);
+    else VCM_K5M(false, true);
+#undef VCM_K5M
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+}  // namespace vcm
+
+extern "C" {
+
+size_t vcm_coeff_grad_workspace_ex(const vcm_tables *h, int B, int I, int M, int precision) {
+    using namespace vcm;
+    size_t need = vcm_coeff_grad_workspace(h, B, I, M);
+    const Tables *t = as_tables(h);
+    MmaGradPlan pl;
+    if (t && precision != VCM_PREC_FP32 && B > 0 && plan_grad_mma(t, B, I, M, &pl) && pl.gy > 1) {
+        const size_t n = (size_t)pl.gy * t->p_out * t->n_max * M;
+        need = n > need ? n : need;
+    }
+    return need;
+}
+
+int vcm_coeff_grad_ex(const vcm_tables *h, const float *dz, const float *x, const float *A, float *dA, float *dG,
+                      float *ws, int B, int I, int M, int precision, void *stream) {
+    using namespace vcm;
+    const Tables *t = as_tables(h);
+    // opt-in: correct in both modes (the whole parity suite passes with VCM_K5_MMA=1) but measured slower than
+    // the fp32 kernel (unpool3: 264 vs 119 us; step +0.43 ms): fragments taken straight from global memory are
+    // 4-byte, sector-granular accesses (5x the L1 sector requests of the 128-bit strip loads, dz read in two
+    // layouts). A tensor-pipe K5 needs dz / x tiles staged in shared memory first (round-2 item).
+    static const int use_mma = [] { const char *e = getenv("VCM_K5_MMA"); return e ? atoi(e) : 0; }();
+    MmaGradPlan pl;
+    if (!use_mma || precision == VCM_PREC_FP32 || t == nullptr || B <= 0 || !plan_grad_mma(t, B, I, M, &pl))
+        return vcm_coeff_grad(h, dz, x, A, dA, dG, ws, B, I, M, stream);
+    VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR_OPT(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
+    VCM_CHECK(dA != nullptr || dG != nullptr, "nothing to compute: dA and dG are both NULL");
+    if (dA != nullptr && pl.gy > 1 && ws == nullptr) return fail(VCM_EINVAL, "workspace required (%d splits)", pl.gy);
+    float *target = dA == nullptr ? nullptr : (pl.gy > 1 ? ws : dA);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool x3 = precision == VCM_PREC_TF32X3;
+    int e = VCM_OK;
+    switch (pl.nt16) {
+        case 1: e = x3 ? launch_grad_mma<1, true>(t, pl, dz, x, A, target, dG, B, I, M, st) : launch_grad_mma<1, false>(t, pl, dz, x, A, target, dG, B, I, M, st); break;
+        case 2: e = x3 ? launch_grad_mma<2, true>(t, pl, dz, x, A, target, dG, B, I, M, st) : launch_grad_mma<2, false>(t, pl, dz, x, A, target, dG, B, I, M, st); break;
+        case 3: e = x3 ? launch_grad_mma<3, true>(t, pl, dz, x, A, target, dG, B, I, M, st) : launch_grad_mma<3, false>(t, pl, dz, x, A, target, dG, B, I, M, st); break;
+        default: e = x3 ? launch_grad_mma<4, true>(t, pl, dz, x, A, target, dG, B, I, M, st) : launch_grad_mma<4, false>(t, pl, dz, x, A, target, dG, B, I, M, st); break;
+    }
+    if (e) return e;
+    if (dA != nullptr && pl.gy > 1) {
+        const size_t n_dA = (size_t)t->p_out * t->n_max * M;
+        sum_splits_kernel<<<(unsigned)ceil_div((int64_t)n_dA, 256), 256, 0, st>>>(ws, dA, n_dA, pl.gy);
+        VCM_LAUNCH_CHECK();
+    }
+    return VCM_OK;
+}
+
+}  // extern "C"

@@ -89,6 +89,7 @@ class _GatherContract(torch.autograd.Function):
                       tag="P%d>%d I%d M%d" % (p_in, tables.p_out, I, M))
         ctx.save_for_backward(x, A)
         ctx.tables = tables
+        ctx.precision = _precision
         ctx.dA_target = _grad_target(A) if A.requires_grad else None
         return z
 
@@ -106,12 +107,13 @@ class _GatherContract(torch.autograd.Function):
         direct_dA = need_dA and ctx.dA_target is not None
         dA = (ctx.dA_target if direct_dA else torch.empty_like(A)) if need_dA else None
         dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
-        n_ws = L.vcm_coeff_grad_workspace(t.handle, B, I, M) if need_dA else 0
+        n_ws = L.vcm_coeff_grad_workspace_ex(t.handle, B, I, M, ctx.precision) if need_dA else 0
         ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
         st = _lib.stream_ptr()
         nnz, tag = t.nnz, "P%d>%d I%d M%d" % (p_in, t.p_out, I, M)
         gb = 4 * B * nnz * I
-        _lib.call("vcm_coeff_grad", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M, st,
+        _lib.call("vcm_coeff_grad_ex", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M,
+                  ctx.precision, st,
                   nbytes=4 * (dz.numel() + (x.numel() if need_dA else 0) + (2 if need_dA else 1) * nnz * M + nnz) +
                   (gb if need_dx else 0),
                   flops=2 * (int(need_dx) + int(need_dA)) * B * nnz * M * I, tag=tag)
