@@ -356,7 +356,7 @@ def roofline(trainer, resident, n_rot, steps, dump=""):
     traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-        if tr["kernel"] == top:
+        if tr["kernel"] in (top, top[:-3] if top.endswith("_ex") else top):
             traffic = tr["ratio"] * v["bytes"] / v["calls"]
             traffic_src = "%s: %.1f MB measured vs %.1f MB algorithmic on %s" % (
                 tr["source"], tr["dram_bytes"] / 1e6, tr["algorithmic_bytes"] / 1e6, tr["layer"])

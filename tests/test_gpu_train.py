@@ -73,6 +73,41 @@ def test_checkpoint_layout_roundtrip():
     assert torch.equal(model.losses(pc, nor, eps)[0], model2.losses(pc, nor, eps)[0])
 
 
+def test_save_load_resumes_identically(tmp_path):
+    """save() writes the reference's file name/keys; load() restores parameters, Adam moments,
+    step and lr, so a resumed run takes bit-identical steps."""
+    model, pc, nor = _small_model(1)
+    tr = T.DataParallelTrainer(model, lr=2e-3)
+    eps = torch.randn(4, model.nrpt_latent, 8, device="cuda")
+    for _ in range(3):
+        tr.step(pc, nor, eps=eps)
+    path = tr.save(str(tmp_path / "weight_00"), 3)
+    assert path.endswith("model_0000003_best.weight")
+    model2, _, _ = _small_model(2)
+    tr2 = T.DataParallelTrainer(model2, lr=1e-4)
+    tr2.load(path)
+    assert tr2.step_count == 3 and abs(tr2.lr - 2e-3) < 1e-12
+    tr.step(pc, nor, eps=eps)
+    tr2.step(pc, nor, eps=eps)
+    assert torch.equal(tr.flat.flat_p, tr2.flat.flat_p)
+
+
+def test_fit_loop_follows_reference_schedule(tmp_path):
+    """fit(): iteration counter, checkpoint cadence/file names and per-epoch lr decay of the
+    reference loop (graphVAE_train.py:303-353)."""
+    import types
+    model, pc, nor = _small_model(1)
+    tr = T.DataParallelTrainer(model, lr=1e-3)
+    param = types.SimpleNamespace(start_iter=10, end_iter=15, evaluate_iter=2,
+                                  write_weight_folder=str(tmp_path / "w") + "/")
+    seen = []
+    end = tr.fit(param, [[(pc, nor)] * 4, [(pc, nor)] * 4, [(pc, nor)] * 4], log=lambda it, l, p: seen.append(it))
+    assert seen == [10, 11, 12, 13, 14, 15] and end == 16 and tr.step_count == 6
+    import os
+    assert sorted(os.listdir(param.write_weight_folder)) == ["model_00000%02d_best.weight" % i for i in (10, 12, 14)]
+    assert abs(tr.lr - 1e-3 * 0.99 ** 2) < 1e-12 and abs(tr.opt_state[1].item() - tr.lr) < 1e-9
+
+
 def test_graph_captured_step_matches_eager():
     """The CUDA-graph replay of the step produces the same parameters as eager steps
     (fixed eps is not used: the encoder's N(0,1) draw comes from the graph-safe generator,

@@ -8,6 +8,6 @@ def __getattr__(name):
     # lazy: importing the package must not require torch / a GPU (build.py, graph_sampling)
     import importlib
     if name in ("graphVAESSW", "functional", "connectivity", "graph_sampling", "synthetic", "build",
-                "graphVAE_train", "_lib"):
+                "graphVAE_train", "graphAE_param_iso", "_lib"):
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

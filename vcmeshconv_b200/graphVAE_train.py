@@ -170,6 +170,7 @@ class DataParallelTrainer:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.flat = FlatBuffers(model.trainable_parameters(), bucket_bytes)
         self.exp_avg = torch.zeros_like(self.flat.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat.flat_p)
@@ -320,6 +321,50 @@ class DataParallelTrainer:
                 "mcvcoeffsdec_dict": m.mcvcoeffsdec.state_dict(), "mcvcoeffsenc_dict": m.mcvcoeffsenc.state_dict(),
                 "optimizer_state_dict": {"step": self.step_count, "lr": self.lr, "exp_avg": self.exp_avg,
                                          "exp_avg_sq": self.exp_avg_sq}}
+
+    def save(self, folder, iteration):
+        """Writes `model_%07d_best.weight` exactly as the reference does (graphVAE_train.py:341-347)."""
+        os.makedirs(folder, exist_ok=True)
+        path = os.path.join(folder, "model_%07d" % iteration + "_best.weight")
+        torch.save(self.state_dict(), path)
+        return path
+
+    def load(self, path):
+        """Loads a checkpoint written by this trainer or by the reference (its optimizer state, a
+        torch.optim.Adam state_dict over per-tensor moments, is not converted: moments restart at zero)."""
+        ckpt = torch.load(path, map_location=self.flat.flat_p.device)
+        self.load_model_state(ckpt)
+        opt = ckpt.get("optimizer_state_dict", {})
+        if "exp_avg" in opt and opt["exp_avg"].numel() == self.exp_avg.numel():
+            with torch.no_grad():
+                self.exp_avg.copy_(opt["exp_avg"])
+                self.exp_avg_sq.copy_(opt["exp_avg_sq"])
+                self.opt_state[0] = float(opt.get("step", 0))
+                self.set_lr(float(opt.get("lr", self.lr)))
+        return ckpt
+
+    def fit(self, param, epochs_of_batches, log=None, gamma=0.99):
+        """The reference's outer loop (graphVAE_train.py:303-353) over an iterable of epochs, each an
+        iterable of (pc, nor) device batches: iteration counter from `start_iter` to `end_iter`,
+        checkpoint every `evaluate_iter` iterations into `write_weight_folder` (rank 0 only), and the
+        ExponentialLR(gamma) decay once per epoch. `log(iteration, loss, parts)` replaces its prints."""
+        iteration = int(getattr(param, "start_iter", 0))
+        end_iter = int(getattr(param, "end_iter", 1 << 62))
+        every = int(getattr(param, "evaluate_iter", 0))
+        for batches in epochs_of_batches:
+            for pc, nor in batches:
+                loss, parts = self.step(pc, nor)
+                if log is not None:
+                    log(iteration, loss, parts)
+                if every and iteration % every == 0 and self.rank == 0:
+                    self.save(param.write_weight_folder, iteration)
+                iteration += 1
+                if iteration > end_iter:
+                    break
+            self.set_lr(self.lr * gamma)
+            if iteration > end_iter:
+                break
+        return iteration
 
     def load_model_state(self, ckpt):
         m = self.model
