@@ -173,6 +173,19 @@ VCM_API int vcm_basis_fwd(const float *z, const float *W, const float *bias, int
                           const float *res, float *y_act, float *out, float *workspace, int B, int P_out, int M,
                           int I, int O, int act, float scale_y, float scale_res, int precision, void *stream);
 
+/* K1 + K2 in ONE launch (graphVAESSW.py:111-138,161): the contraction z = sum_n A[p,n,m] x[b,idx[p,n],i] is
+ * produced tile by tile in shared memory in the tensor-core operand layout and consumed there, so z makes no
+ * HBM round trip. `z` (fp32 [B,P_out,M*I]) is optional: pass a buffer when the backward pass needs it (written
+ * once by TMA stores), NULL for inference. Everything else as vcm_basis_fwd. Available for precision
+ * VCM_PREC_TF32, B % 16 == 0, B <= 128, M <= 17, I % 8 == 0, O % 32 == 0 (vcm_conv_fwd_fused_supported);
+ * other shapes use vcm_gather_contract_fwd + vcm_basis_fwd. */
+VCM_API int vcm_conv_fwd_fused_supported(const vcm_tables *t, int B, int M, int I, int O, int precision);
+VCM_API size_t vcm_conv_fwd_fused_workspace(const vcm_tables *t, int B, int M, int I, int O, int precision);
+VCM_API int vcm_conv_fwd_fused(const vcm_tables *t, const float *x, const float *A, const float *W,
+                               const float *bias, int bias_per_point, const float *res, float *y_act, float *out,
+                               float *z, float *workspace, int B, int M, int I, int O, int act, float scale_y,
+                               float scale_res, int precision, void *stream);
+
 /* The K2 epilogue as a stand-alone pass (used when the basis projection runs
  * before the gather, i.e. for layers whose M*O is narrower than I):
  *   out = (act ? ELU : id)(s + bias) * scale_y + (res ? res * scale_res : 0)

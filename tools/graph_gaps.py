@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Idle time between kernels inside the CUDA-graph replay of one training step (torch.profiler / CUPTI timestamps):
+span of a replay vs the sum of its kernels' durations, and the gap histogram."""
+import os, sys, json, tempfile
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from vcmeshconv_b200 import functional as F_, graphVAE_train as T
+
+F_.set_precision(os.environ.get("VCM_PRECISION", "tf32"))
+pts, faces, tabs, nums = bench.build_tables(6890)
+enc = [tabs["pool%d" % l] for l in range(1, 7)]; dec = [tabs["unpool%d" % l] for l in range(6, 0, -1)]
+torch.manual_seed(0)
+model = T.Net_autoenc(T.make_param(enc, dec, tabs["pool0"], 6890, 0.9), faces).cuda()
+tr = T.DataParallelTrainer(model)
+pc, nor = bench.synthetic_batch(pts, faces, 16, 0)
+pc, nor = torch.from_numpy(pc).cuda(), torch.from_numpy(nor).cuda()
+tr.capture(pc, nor)
+for _ in range(5): tr.step(pc, nor)
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+NREP = 4
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(NREP):
+        tr.step(pc, nor)
+        torch.cuda.synchronize()
+fn = os.path.join(tempfile.mkdtemp(), "t.json")
+prof.export_chrome_trace(fn)
+ev = [e for e in json.load(open(fn))["traceEvents"] if e.get("cat") == "kernel"]
+ev.sort(key=lambda e: e["ts"])
+per = len(ev) // NREP
+print("kernels per replay:", per)
+for r in range(NREP):
+    k = ev[r * per:(r + 1) * per]
+    span = k[-1]["ts"] + k[-1]["dur"] - k[0]["ts"]
+    busy = sum(e["dur"] for e in k)
+    gaps = [k[i + 1]["ts"] - (k[i]["ts"] + k[i]["dur"]) for i in range(len(k) - 1)]
+    pos = [g for g in gaps if g > 0]
+    print("replay %d: span %.1f us, sum of kernel durations %.1f us, idle %.1f us (%d gaps, median %.2f us, max %.1f us), overlapped %d"
+          % (r, span, busy, sum(pos), len(pos), sorted(pos)[len(pos) // 2] if pos else 0, max(pos) if pos else 0,
+             sum(1 for g in gaps if g <= 0)))
+k = ev[(NREP - 1) * per:]
+small = sum(1 for e in k if e["dur"] < 5); print("kernels < 5 us: %d (sum %.1f us)" % (small, sum(e["dur"] for e in k if e["dur"] < 5)))
+agg = {}
+for e in k:
+    n = e["name"].split("<")[0].split("(")[0][-60:]
+    a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += e["dur"]
+for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+    print("%8.1f us x%-3d %s" % (t, c, n))

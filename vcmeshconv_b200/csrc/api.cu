@@ -83,4 +83,34 @@ int vcm_basis_bwd_dw(const float *ds, const float *z, float *dW, float *workspac
     return simt_basis_bwd_dw(ds, z, dW, workspace, rows, M, I, O, st);
 }
 
+int vcm_conv_fwd_fused_supported(const vcm_tables *tables, int B, int M, int I, int O, int precision) {
+    const Tables *t = as_tables(tables);
+    return t != nullptr && B > 0 && fused_fwd_supported(t, B, M, I, O, precision) ? 1 : 0;
+}
+
+size_t vcm_conv_fwd_fused_workspace(const vcm_tables *tables, int B, int M, int I, int O, int precision) {
+    const Tables *t = as_tables(tables);
+    if (t == nullptr || B <= 0 || !fused_fwd_supported(t, B, M, I, O, precision)) return 0;
+    return fused_fwd_workspace(t, B, M, I, O);
+}
+
+int vcm_conv_fwd_fused(const vcm_tables *tables, const float *x, const float *A, const float *W, const float *bias,
+                       int bias_per_point, const float *res, float *y_act, float *out, float *z, float *workspace,
+                       int B, int M, int I, int O, int act, float scale_y, float scale_res, int precision,
+                       void *stream) {
+    const Tables *t = as_tables(tables);
+    VCM_CHECK(t != nullptr, "tables handle is NULL");
+    VCM_CHECK(B > 0, "bad batch");
+    if (int e = check_gemm((int64_t)B * t->p_out, M, I, O, precision)) return e;
+    VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR(W); VCM_DEVPTR(out);
+    VCM_DEVPTR_OPT(bias); VCM_DEVPTR_OPT(res); VCM_DEVPTR_OPT(y_act); VCM_DEVPTR_OPT(z); VCM_DEVPTR_OPT(workspace);
+    VCM_CHECK(aligned16(x) && aligned16(W) && aligned16(out) && (z == nullptr || aligned16(z)),
+              "x, W, out and z must be 16-byte aligned");
+    if (!fused_fwd_supported(t, B, M, I, O, precision))
+        return fail(VCM_EUNSUPPORTED, "vcm_conv_fwd_fused: unsupported shape/precision (query vcm_conv_fwd_fused_supported)");
+    if (t->p_out == 0) return VCM_OK;
+    return fused_fwd(t, x, A, W, bias, bias_per_point, res, y_act, out, z, workspace, B, M, I, O, act, scale_y,
+                     scale_res, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -29,4 +29,14 @@ size_t tc_basis_bwd_dw_workspace(int64_t R, int M, int I, int O, int precision);
 int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64_t R, int M, int I, int O,
                     int precision, cudaStream_t st);
 
+int splitk_fwd_epilogue(const float *part, int n_split, int64_t R, int O, int P_out, const float *bias, int per_point,
+                        const float *res, float *y_act, float *out, int act, float sy, float sr, cudaStream_t st);
+
+// K1 + K2 fused (fused_fwd.cu)
+bool fused_fwd_supported(const Tables *t, int B, int M, int I, int O, int precision);
+size_t fused_fwd_workspace(const Tables *t, int B, int M, int I, int O);
+int fused_fwd(const Tables *t, const float *x, const float *A, const float *W, const float *bias, int per_point,
+              const float *res, float *y_act, float *out, float *z, float *ws, int B, int M, int I, int O, int act,
+              float sy, float sr, cudaStream_t st);
+
 }  // namespace vcm

@@ -96,33 +96,38 @@ class _GatherContract(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz):
         x, A = ctx.saved_tensors
-        t = ctx.tables
-        B, p_in, I = x.shape
-        M = A.shape[2]
         need_dx, need_dA = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if not (need_dx or need_dA) or B == 0:
-            return (torch.zeros_like(x) if need_dx else None), (torch.zeros_like(A) if need_dA else None), None
-        dz = _req(dz, "dz")
-        L = _lib.lib()
-        direct_dA = need_dA and ctx.dA_target is not None
-        dA = (ctx.dA_target if direct_dA else torch.empty_like(A)) if need_dA else None
-        dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
-        n_ws = L.vcm_coeff_grad_workspace_ex(t.handle, B, I, M, ctx.precision) if need_dA else 0
-        ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
-        st = _lib.stream_ptr()
-        nnz, tag = t.nnz, "P%d>%d I%d M%d" % (p_in, t.p_out, I, M)
-        gb = 4 * B * nnz * I
-        _lib.call("vcm_coeff_grad_ex", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M,
-                  ctx.precision, st,
-                  nbytes=4 * (dz.numel() + (x.numel() if need_dA else 0) + (2 if need_dA else 1) * nnz * M + nnz) +
-                  (gb if need_dx else 0),
-                  flops=2 * (int(need_dx) + int(need_dA)) * B * nnz * M * I, tag=tag)
-        dx = None
-        if need_dx:
-            dx = torch.empty_like(x)
-            _lib.call("vcm_scatter_rev", t.handle, _ptr(dG), _ptr(dx), B, I, 0, st,
-                      nbytes=gb + 4 * nnz + 4 * (p_in + 1) + 4 * x.numel(), flops=B * nnz * I, tag=tag)
-        return dx, (dA if need_dA and not direct_dA else None), None
+        dx, dA = _gather_backward(ctx.tables, x, A, dz, need_dx, need_dA, ctx.dA_target, ctx.precision)
+        return dx, dA, None
+
+
+def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
+    """K5 (+ K6): (dx, dA) of z = gather_contract(x, A); dA is None when it was written into `dA_target`."""
+    B, p_in, I = x.shape
+    M = A.shape[2]
+    if not (need_dx or need_dA) or B == 0:
+        return (torch.zeros_like(x) if need_dx else None), (torch.zeros_like(A) if need_dA else None)
+    dz = _req(dz, "dz")
+    L = _lib.lib()
+    direct_dA = need_dA and dA_target is not None
+    dA = (dA_target if direct_dA else torch.empty_like(A)) if need_dA else None
+    dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
+    n_ws = L.vcm_coeff_grad_workspace_ex(t.handle, B, I, M, precision) if need_dA else 0
+    ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
+    st = _lib.stream_ptr()
+    nnz, tag = t.nnz, "P%d>%d I%d M%d" % (p_in, t.p_out, I, M)
+    gb = 4 * B * nnz * I
+    _lib.call("vcm_coeff_grad_ex", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M,
+              precision, st,
+              nbytes=4 * (dz.numel() + (x.numel() if need_dA else 0) + (2 if need_dA else 1) * nnz * M + nnz) +
+              (gb if need_dx else 0),
+              flops=2 * (int(need_dx) + int(need_dA)) * B * nnz * M * I, tag=tag)
+    dx = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        _lib.call("vcm_scatter_rev", t.handle, _ptr(dG), _ptr(dx), B, I, 0, st,
+                  nbytes=gb + 4 * nnz + 4 * (p_in + 1) + 4 * x.numel(), flops=B * nnz * I, tag=tag)
+    return dx, (dA if need_dA and not direct_dA else None)
 
 
 class _ProjectGather(torch.autograd.Function):
@@ -205,58 +210,114 @@ class _BasisGemm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         z, W, y = ctx.saved_tensors
-        M, I, O, act, sy, sr, precision, per_point, has_bias, has_res = ctx.cfg
-        B, p_out, K = z.shape
-        need_dz, need_dW, need_db, need_dres = (ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                                has_bias and ctx.needs_input_grad[2],
-                                                has_res and ctx.needs_input_grad[3])
-        dout = _req(dout, "dout")
-        L = _lib.lib()
-        st = _lib.stream_ptr()
-        dev = z.device
-        if B == 0 or p_out == 0:
-            return (torch.zeros_like(z), torch.zeros_like(W),
-                    (torch.zeros(p_out, O, device=dev) if per_point else torch.zeros(O, device=dev)) if need_db else None,
-                    torch.zeros_like(dout) if need_dres else None) + (None,) * 7
-        ds = torch.empty_like(dout)
-        direct_db = need_db and ctx.db_target is not None
-        db_pp = None
-        if need_db:
-            db_pp = ctx.db_target if (direct_db and per_point) else torch.empty(p_out, O, device=dev, dtype=torch.float32)
-        dres = torch.empty_like(dout) if need_dres else None
-        ny = dout.numel()
-        tag = "R%d K%d O%d" % (B * p_out, K, O)
-        _lib.call("vcm_act_bwd", _ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st,
-                  nbytes=4 * (ny * (2 + (1 if act else 0) + (1 if need_dres else 0)) + (p_out * O if need_db else 0)),
-                  flops=2 * ny, tag=tag)
-        dbias = None
-        if need_db:
-            if per_point:
-                dbias = db_pp
-            else:
-                dbias = ctx.db_target if direct_db else torch.empty(O, device=dev, dtype=torch.float32)
-                _lib.call("vcm_colsum", _ptr(db_pp), _ptr(dbias), p_out, O, st, nbytes=4 * (p_out * O + O),
-                          flops=p_out * O, tag=tag)
-            if direct_db:
-                dbias = None
-        R = B * p_out
-        dz = dW = None
-        if need_dz:
-            dz = torch.empty_like(z)
-            n_ws = L.vcm_basis_bwd_dz_workspace(R, M, I, O, precision)
-            ws = torch.empty(n_ws, device=dev, dtype=torch.float32) if n_ws else None
-            _lib.call("vcm_basis_bwd_dz", _ptr(ds), _ptr(W), _ptr(dz), _ptr(ws), R, M, I, O, 0, precision, st,
-                      nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
-        if need_dW:
-            direct_dW = ctx.dW_target is not None
-            dW = ctx.dW_target if direct_dW else torch.empty_like(W)
-            n_ws = L.vcm_basis_bwd_dw_workspace(R, M, I, O, precision)
-            ws = torch.empty(max(n_ws, 1), device=dev, dtype=torch.float32)
-            _lib.call("vcm_basis_bwd_dw", _ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision, st,
-                      nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
-            if direct_dW:
-                dW = None
-        return (dz, dW, dbias, dres) + (None,) * 7
+        has_bias, has_res = ctx.cfg[8], ctx.cfg[9]
+        need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2],
+                has_res and ctx.needs_input_grad[3])
+        return _basis_backward(z, W, y, dout, ctx.cfg, need, ctx.dW_target, ctx.db_target) + (None,) * 7
+
+
+def _basis_backward(z, W, y, dout, cfg, need, dW_target, db_target):
+    """act_bwd + K3 + K4: (dz, dW, dbias, dres) of out = basis_gemm(z, W, bias, res); gradients written into a
+    `*_target` come back as None."""
+    M, I, O, act, sy, sr, precision, per_point, has_bias, has_res = cfg
+    need_dz, need_dW, need_db, need_dres = need
+    B, p_out, K = z.shape
+    dout = _req(dout, "dout")
+    L = _lib.lib()
+    st = _lib.stream_ptr()
+    dev = z.device
+    if B == 0 or p_out == 0:
+        return (torch.zeros_like(z), torch.zeros_like(W),
+                (torch.zeros(p_out, O, device=dev) if per_point else torch.zeros(O, device=dev)) if need_db else None,
+                torch.zeros_like(dout) if need_dres else None)
+    ds = torch.empty_like(dout)
+    direct_db = need_db and db_target is not None
+    db_pp = None
+    if need_db:
+        db_pp = db_target if (direct_db and per_point) else torch.empty(p_out, O, device=dev, dtype=torch.float32)
+    dres = torch.empty_like(dout) if need_dres else None
+    ny = dout.numel()
+    tag = "R%d K%d O%d" % (B * p_out, K, O)
+    _lib.call("vcm_act_bwd", _ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st,
+              nbytes=4 * (ny * (2 + (1 if act else 0) + (1 if need_dres else 0)) + (p_out * O if need_db else 0)),
+              flops=2 * ny, tag=tag)
+    dbias = None
+    if need_db:
+        if per_point:
+            dbias = db_pp
+        else:
+            dbias = db_target if direct_db else torch.empty(O, device=dev, dtype=torch.float32)
+            _lib.call("vcm_colsum", _ptr(db_pp), _ptr(dbias), p_out, O, st, nbytes=4 * (p_out * O + O),
+                      flops=p_out * O, tag=tag)
+        if direct_db:
+            dbias = None
+    R = B * p_out
+    dz = dW = None
+    if need_dz:
+        dz = torch.empty_like(z)
+        n_ws = L.vcm_basis_bwd_dz_workspace(R, M, I, O, precision)
+        ws = torch.empty(n_ws, device=dev, dtype=torch.float32) if n_ws else None
+        _lib.call("vcm_basis_bwd_dz", _ptr(ds), _ptr(W), _ptr(dz), _ptr(ws), R, M, I, O, 0, precision, st,
+                  nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
+    if need_dW:
+        direct_dW = dW_target is not None
+        dW = dW_target if direct_dW else torch.empty_like(W)
+        n_ws = L.vcm_basis_bwd_dw_workspace(R, M, I, O, precision)
+        ws = torch.empty(max(n_ws, 1), device=dev, dtype=torch.float32)
+        _lib.call("vcm_basis_bwd_dw", _ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision, st,
+                  nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
+        if direct_dW:
+            dW = None
+    return dz, dW, dbias, dres
+
+
+class _FusedConv(torch.autograd.Function):
+    """out = epi(gather_contract(x, A) @ stacked(W)) in one launch (vcm_conv_fwd_fused): z is produced on chip and
+    only written to HBM (once) when a backward pass will need it."""
+
+    @staticmethod
+    def forward(ctx, x, A, W, bias, res, tables, M, I, O, act, scale_y, scale_res, precision):
+        x, A, W = _req(x, "x"), _req(A, "coefficients"), _req(W, "weights")
+        B, p_in, _ = x.shape
+        p_out = tables.p_out
+        per_point = 0
+        if bias is not None:
+            bias = _req(bias, "bias")
+            per_point = 1 if bias.dim() == 2 else 0
+        if res is not None:
+            res = _req(res, "residual")
+        out = torch.empty(B, p_out, O, device=x.device, dtype=torch.float32)
+        y_act = torch.empty_like(out) if act and (res is not None or scale_y != 1.0) else None
+        z = torch.empty(B, p_out, M * I, device=x.device, dtype=torch.float32) if any(ctx.needs_input_grad[:5]) else None
+        n_ws = _lib.lib().vcm_conv_fwd_fused_workspace(tables.handle, B, M, I, O, precision)
+        ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
+        nnz = tables.nnz
+        _lib.call("vcm_conv_fwd_fused", tables.handle, _ptr(x), _ptr(A), _ptr(W), _ptr(bias), per_point, _ptr(res),
+                  _ptr(y_act), _ptr(out), _ptr(z), _ptr(ws), B, M, I, O, int(act), scale_y, scale_res, precision,
+                  _lib.stream_ptr(),
+                  nbytes=4 * (x.numel() + nnz * M + nnz + W.numel() + out.numel() * (2 if res is not None else 1) +
+                              (z.numel() if z is not None else 0) + (y_act.numel() if y_act is not None else 0)),
+                  flops=2 * B * nnz * M * I + 2 * B * p_out * M * I * O,
+                  tag="P%d>%d I%d O%d" % (p_in, p_out, I, O))
+        y_saved = (y_act if y_act is not None else out) if act else None
+        ctx.save_for_backward(x, A, W, z, y_saved)
+        ctx.tables = tables
+        ctx.cfg = (M, I, O, int(act), scale_y, scale_res, precision, per_point, bias is not None, res is not None)
+        ctx.dA_target = _grad_target(A) if A.requires_grad else None
+        ctx.dW_target = _grad_target(W) if W.requires_grad else None
+        ctx.db_target = _grad_target(bias) if bias is not None and bias.requires_grad else None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, A, W, z, y = ctx.saved_tensors
+        has_bias, has_res = ctx.cfg[8], ctx.cfg[9]
+        need_dx, need_dA = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need = (need_dx or need_dA, ctx.needs_input_grad[2], has_bias and ctx.needs_input_grad[3],
+                has_res and ctx.needs_input_grad[4])
+        dz, dW, dbias, dres = _basis_backward(z, W, y, dout, ctx.cfg, need, ctx.dW_target, ctx.db_target)
+        dx, dA = _gather_backward(ctx.tables, x, A, dz, need_dx, need_dA, ctx.dA_target, ctx.cfg[6])
+        return (dx, dA, dW, dbias, dres) + (None,) * 8
 
 
 class _BiasAct(torch.autograd.Function):
@@ -353,6 +414,17 @@ def basis_gemm(z, weights, bias, res, M, I, O, act, scale_y=1.0, scale_res=0.0, 
     """out = (act ? ELU : id)(z @ stacked(weights) + bias) * scale_y + res * scale_res."""
     return _BasisGemm.apply(z, weights, bias, res, M, I, O, bool(act), float(scale_y), float(scale_res),
                             _precision if precision is None else precision)
+
+
+def fused_conv_supported(tables, B, M, I, O, precision=None):
+    prec = _precision if precision is None else precision
+    return bool(_lib.lib().vcm_conv_fwd_fused_supported(tables.handle, B, M, I, O, prec))
+
+
+def fused_conv(x, coeffs, weights, bias, res, tables, M, I, O, act, scale_y=1.0, scale_res=0.0, precision=None):
+    """basis_gemm(gather_contract(x, coeffs, tables), ...) in one launch; check fused_conv_supported first."""
+    return _FusedConv.apply(x, coeffs, weights, bias, res, tables, M, I, O, bool(act), float(scale_y),
+                            float(scale_res), _precision if precision is None else precision)
 
 
 def bias_act(s, bias, res, act, scale_y=1.0, scale_res=0.0):
