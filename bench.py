@@ -114,24 +114,30 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of the reference, on the host cores
 # ---------------------------------------------------------------------------------
-def cpu_reference_run(args, steps, warmup, tabs, pts, faces):
+def cpu_reference_run(args, steps, warmup, tabs, pts, faces, device="cpu"):
+    """`device="cuda"` runs the same restatement (the reference's ATen op sequence: index_select, einsum, sum, elu,
+    autograd) on the GPU: the reference's own stock GPU path, as a second, stronger reported baseline."""
     import torch
     from oracle import vcconv_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     enc = [tabs["pool%d" % l] for l in range(1, 7)]
     dec = [tabs["unpool%d" % l] for l in range(6, 0, -1)]
     ae = orc.AutoEncoder(enc, dec, len(pts), tabs["pool0"], faces, residual_rate=RESIDUAL, seed=0).requires_grad_(True)
+    ae = ae.to(device)
     opt = torch.optim.Adam(ae.parameters(), lr=1e-4, betas=(0.9, 0.999))    # graphVAE_train.py:260
     pc, nor = synthetic_batch(pts, faces, args.batch, 0)
-    pc, nor = torch.from_numpy(pc), torch.from_numpy(nor)
+    pc, nor = torch.from_numpy(pc).to(device), torch.from_numpy(nor).to(device)
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
     times = []
     for it in range(warmup + steps):
+        sync()
         t0 = time.perf_counter()
-        eps = torch.randn(args.batch, *ae.latent_shape)
+        eps = torch.randn(args.batch, *ae.latent_shape, device=device)
         loss = ae.losses(pc, nor, eps)[0]
         opt.zero_grad()
         loss.backward()
         opt.step()
+        sync()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     mean = sum(times) / len(times)
@@ -292,6 +298,15 @@ def run_ours(args):
         cpu = {"value": v, "unit": "meshes/s", "cores": cores, "kind": "port", "ms_per_step": cms,
                "sample": "1 warm-up + %d timed full steps (fwd+bwd+Adam, batch %d) of oracle/vcconv_oracle.py on "
                          "the host cores" % (args.cpu_steps, args.batch)}
+    aten = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, ams, _ = cpu_reference_run(args, 10, 3, tabs, pts, faces, device="cuda")
+            aten = {"value": v, "unit": "meshes/s", "ms_per_step": ams, "kind": "port",
+                    "what": "oracle/vcconv_oracle.py (the reference's ATen op sequence, fp32, eager autograd, "
+                            "torch.optim.Adam) on this GPU: 3 warm-up + 10 timed steps, batch %d" % args.batch}
+        except Exception as e:                                   # a reported baseline must not fail the bench
+            aten = {"unavailable": repr(e)[:200]}
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "meshes/s", "n_gpus": world, "steps": args.steps,
@@ -306,7 +321,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "meshes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "fp32_mode": fp32_mode,
+            "fp32_mode": fp32_mode, "aten_gpu_baseline": aten,
             "kernel_breakdown": breakdown}))
     if world > 1:
         dist.barrier()

@@ -78,13 +78,13 @@ def vcconv_forward(x, coeffs, weights, bias, ids, in_point_num, *, is_final_laye
     cout = weights.shape[1] // cin
 
     # :111-113  sentinel mask obtained by gathering a ones-vector whose slot P_in is 0
-    ones = torch.ones(p_in + 1, dtype=x.dtype)
+    ones = torch.ones(p_in + 1, dtype=x.dtype, device=x.device)
     ones[p_in] = 0
     mask = _gather_rows(ones, ids, 0).contiguous()                       # [P_out, N]
     # :118
     a_eff = coeffs * mask.view(p_out, nmax, 1)
     # :121-122  zero row appended, then gathered
-    xpad = torch.cat((x, torch.zeros(batch, 1, cin, dtype=x.dtype)), 1)  # [B, P_in+1, I]
+    xpad = torch.cat((x, torch.zeros(batch, 1, cin, dtype=x.dtype, device=x.device)), 1)  # [B, P_in+1, I]
     g = _gather_rows(xpad, ids, 1)                                       # [B, P_out, N, I]
     # :123  stage 1: neighbours -> M basis slots
     z = torch.einsum('pnm,bpni->bpmi', a_eff, g)                         # [B, P_out, M, I]
@@ -123,12 +123,12 @@ def vcconv_forward_edge_kernels(x, coeffs, weights, bias, ids, in_point_num, *, 
     batch, p_in, cin = x.shape
     p_out, nmax = ids.shape
     cout = weights.shape[1] // cin
-    ones = torch.ones(p_in + 1, dtype=x.dtype)
+    ones = torch.ones(p_in + 1, dtype=x.dtype, device=x.device)
     ones[p_in] = 0
     mask = ones[ids].contiguous()
     a_eff = coeffs * mask.view(p_out, nmax, 1)
     k = torch.einsum('pnm,mc->pnc', a_eff, weights).view(p_out, nmax, cout, cin)   # :192-193
-    xpad = torch.cat((x, torch.zeros(batch, 1, cin, dtype=x.dtype)), 1)
+    xpad = torch.cat((x, torch.zeros(batch, 1, cin, dtype=x.dtype, device=x.device)), 1)
     g = xpad[:, ids]                                                               # :197
     y = torch.einsum('pnoi,bpni->bpno', k, g).sum(2) + bias                        # :199-207
     return y if is_final_layer else F.elu(y)
@@ -213,7 +213,7 @@ def _laplacian(pc, ids0, counts0):
     """cnt_p * x_self - sum of the other neighbours, over the layer-0 table
     whose first entry is the vertex itself (graphVAESSW.py:515-525)."""
     batch, n, _ = pc.shape
-    pad = torch.cat((pc, torch.zeros(batch, 1, 3, dtype=pc.dtype)), 1)
+    pad = torch.cat((pc, torch.zeros(batch, 1, 3, dtype=pc.dtype, device=pc.device)), 1)
     lap = pad[:, ids0[:, 0]] * counts0.to(pc.dtype).view(1, n, 1).repeat(batch, 1, 3)
     for k in range(1, ids0.shape[1]):
         lap = lap - pad[:, ids0[:, k]]
@@ -296,6 +296,15 @@ class AutoEncoder:
     def requires_grad_(self, flag=True):
         for p in self.parameters():
             p.requires_grad_(flag)
+        return self
+
+    def to(self, device):
+        """Moves parameters and tables (bench.py's ATen-on-GPU baseline; everything else runs on the CPU)."""
+        for p in self.parameters():
+            p.data = p.data.to(device)
+        for lay in self.enc[0] + self.dec[0]:
+            lay.counts, lay.ids = lay.counts.to(device), lay.ids.to(device)
+        self.counts0, self.ids0, self.faces = self.counts0.to(device), self.ids0.to(device), self.faces.to(device)
         return self
 
     def losses(self, x, normals, eps, **kw):

@@ -43,7 +43,8 @@ k = ev[(NREP - 1) * per:]
 small = sum(1 for e in k if e["dur"] < 5); print("kernels < 5 us: %d (sum %.1f us)" % (small, sum(e["dur"] for e in k if e["dur"] < 5)))
 agg = {}
 for e in k:
-    n = e["name"].split("<")[0].split("(")[0][-60:]
+    n = e["name"].replace("vcm::<unnamed>::", "").replace("(anonymous namespace)::", "").replace("void ", "")
+    n = n.split("(")[0][:110] + " g%s" % (e.get("args", {}).get("grid", ""),)
     a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += e["dur"]
-for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
     print("%8.1f us x%-3d %s" % (t, c, n))

@@ -24,7 +24,7 @@ LAYERS = {"enc1": ("pool2", 2, 32, 64), "enc2": ("pool3", 3, 64, 128), "enc3": (
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--layer", default="dec3", choices=sorted(LAYERS))
-    ap.add_argument("--kernel", default="k1", choices=["k1", "k5", "k6", "fwd", "dz", "dw"])
+    ap.add_argument("--kernel", default="k1", choices=["k1", "k5", "k6", "fwd", "dz", "dw", "fused", "fused_noz"])
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--precision", default="tf32")
@@ -51,6 +51,9 @@ def main():
                          L.vcm_basis_bwd_dz_workspace(B * P, M, I, O, prec), L.vcm_basis_fwd_workspace(B * P, M, I, O, prec), 1),
                      device="cuda")
     nnz = t.nnz
+    ws_f = torch.empty(max(L.vcm_conv_fwd_fused_workspace(t.handle, B, M, I, O, prec), 1), device="cuda")
+    fused = lambda zz: L.vcm_conv_fwd_fused(t.handle, x.data_ptr(), A.data_ptr(), W.data_ptr(), None, 0, None, None,
+                                            out.data_ptr(), zz, ws_f.data_ptr(), B, M, I, O, 1, 1.0, 0.0, prec, st)
     X, Z, Ab, Gb, Y, Wb = 4 * x.numel(), 4 * z.numel(), 4 * nnz * M, 4 * B * nnz * I, 4 * out.numel(), 4 * W.numel()
     calls = {
         "k1": (lambda: L.vcm_gather_contract_fwd_ex(t.handle, x.data_ptr(), A.data_ptr(), z.data_ptr(), B, I, M, prec, st),
@@ -65,6 +68,8 @@ def main():
         "dw": (lambda: L.vcm_basis_bwd_dw(ds.data_ptr(), z.data_ptr(), dW.data_ptr(), ws.data_ptr(), B * P, M, I, O, prec,
                                           st), Z + Wb + Y, 2 * B * P * M * I * O),
     }
+    calls["fused"] = (lambda: fused(z.data_ptr()), X + Ab + 4 * nnz + Z + Wb + Y, 2 * B * nnz * M * I + 2 * B * P * M * I * O)
+    calls["fused_noz"] = (lambda: fused(None), X + Ab + 4 * nnz + Wb + Y, 2 * B * nnz * M * I + 2 * B * P * M * I * O)
     fn, nbytes, flops = calls[a.kernel]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(3):

@@ -8,7 +8,7 @@
 // Reduction order: k = (i-chunk of 8, basis m, i within chunk). One "chunk" is 8 input channels of all M bases;
 // it is cut into G = ceil(M/4) k-steps of [4 bases x 8 channels] = 32 tf32 = one 128-byte swizzle row.
 //   warps 0-7   producers: thread = (row, half of the 8-channel chunk). Neighbour rows of x arrive through a
-//               per-thread cp.async FIFO (depth 8, no registers held across the L2 latency); coefficients come
+//               per-thread cp.async double buffer (bursts of <= 8, no registers held across the L2 latency); coefficients come
 //               from shared memory pre-duplicated as (a, a) pairs so that the contraction is pure FFMA2; at the
 //               end of a chunk the 17 x 4 accumulators are written into the A stages (SWIZZLE_128B, K-major).
 //               With STORE_Z the same registers also go to z[b][p][m][i] (16-byte streaming stores).
@@ -27,11 +27,11 @@ namespace {
 
 constexpr int FF_PRODUCERS = 256;
 constexpr int FF_THREADS = FF_PRODUCERS + 96;
-constexpr int FF_PD = 8;                       // gather FIFO depth (neighbours in flight per thread)
+constexpr int FF_SEG = 8;                      // neighbours per gather burst (two bursts resident per thread)
 constexpr int FF_MT = 17;                      // bases accumulated per thread
 constexpr int FF_MP = 18;                      // padded to pairs
 constexpr int FF_G = (FF_MT + 3) / 4;          // k-steps per chunk at M = 17
-constexpr int FF_FIFO_BYTES = FF_PD * FF_PRODUCERS * 16;
+constexpr int FF_FIFO_BYTES = 2 * FF_SEG * FF_PRODUCERS * 16;
 
 struct FusedParams {
     const float *x, *A;
@@ -127,51 +127,62 @@ conv_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedPara
         const int l = live ? __ldg(p.last + pv) : 0;                       // warp-uniform (B % 16 == 0)
         const uint32_t idx_v = smem_u32(idx_s) + (uint32_t)((live ? v : 0) * p.n_max) * 4u;
         const uint32_t coef_v = smem_u32(coef_s) + (uint32_t)((live ? v : 0) * p.n_max) * (FF_MP * 8u);
-        const float *xc = p.x + (size_t)b * p.p_in * p.I + h * 4 + c_begin * 8;      // this thread's column of chunk fetch_c
+        const float *xcol = p.x + (size_t)b * p.p_in * p.I + h * 4;       // this thread's 4 channels of chunk 0
         const uint32_t my_fifo = smem_u32(fifo) + (uint32_t)tid * 16u;
 
-        int fetch_n = 0, fetch_c = c_begin, slot = 0;
-        auto issue = [&]() {
-            if (l > 0 && fetch_c < c_end) {
-                const int off = lds32(idx_v + (uint32_t)fetch_n * 4u);
-                const uint32_t dst = my_fifo + (uint32_t)slot * (FF_PRODUCERS * 16);
+        // The neighbour list is cut into segments of <= FF_SEG; the loads of segment k+1 are issued in one burst
+        // (one cp.async group) before segment k is consumed. Two reasons for bursts instead of a rolling
+        // prefetch: the wait is a compile-time wait_group<1>, and the proxy fence of the flush below drains
+        // every outstanding cp.async of the thread - with bursts the youngest one is a whole segment old.
+        const int nseg = (l + FF_SEG - 1) / FF_SEG;
+        const int seg_len = nseg ? (l + nseg - 1) / nseg : 0;
+        auto issue_seg = [&](int c, int sg, int buf) {
+            const int n0 = sg * seg_len, n1 = min(l, n0 + seg_len);
+            const float *xc = xcol + c * 8;
+            uint32_t dst = my_fifo + (uint32_t)(buf * FF_SEG) * (FF_PRODUCERS * 16);
+            for (int n = n0; n < n1; ++n, dst += FF_PRODUCERS * 16) {
+                const int off = lds32(idx_v + (uint32_t)n * 4u);
                 if (off >= 0) cp_async16(dst, xc + off, 16u);
                 else          // padding sentinel: contributes an exact zero
                     asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
-                if (++fetch_n == l) { fetch_n = 0; ++fetch_c; xc += 8; }
             }
-            cp_async_commit();
-            slot = (slot + 1) & (FF_PD - 1);
         };
-#pragma unroll
-        for (int k = 0; k < FF_PD; ++k) issue();
+        if (nseg) issue_seg(c_begin, 0, 0);
+        cp_async_commit();
 
         // z[b][pv][m][i]: this thread's 4 channels of every chunk (only the first N tile writes it)
         float *zrow = (STORE_Z && live && n_tile == 0) ? p.z + ((size_t)b * p.p_out + pv) * p.M * p.I + h * 4 : nullptr;
         const uint32_t row_off = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
-        int step = 0;
+        int step = 0, buf = 0;
         for (int c = c_begin; c < c_end; ++c) {
             float2 acc[FF_MT][2];
 #pragma unroll
             for (int m = 0; m < FF_MT; ++m) acc[m][0] = acc[m][1] = make_float2(0.f, 0.f);
+            for (int sg = 0; sg < nseg; ++sg) {
+                const bool last_seg = sg + 1 == nseg;
+                if (!last_seg || c + 1 < c_end) issue_seg(last_seg ? c + 1 : c, last_seg ? 0 : sg + 1, buf ^ 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+                const int n0 = sg * seg_len, n1 = min(l, n0 + seg_len);
+                uint32_t src = my_fifo + (uint32_t)(buf * FF_SEG) * (FF_PRODUCERS * 16);
+                uint32_t cf = coef_v + (uint32_t)n0 * (FF_MP * 8u);
 #pragma unroll 2
-            for (int n = 0; n < l; ++n) {
-                cp_async_wait<FF_PD - 1>();
-                const float4 xv = lds128(my_fifo + (uint32_t)slot * (FF_PRODUCERS * 16));
-                issue();                                                   // refills the slot just read
-                const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
-                const uint32_t cf = coef_v + (uint32_t)n * (FF_MP * 8u);
+                for (int n = n0; n < n1; ++n, src += FF_PRODUCERS * 16, cf += FF_MP * 8u) {
+                    const float4 xv = lds128(src);
+                    const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
 #pragma unroll
-                for (int k = 0; k < FF_MP / 2; ++k) {
-                    const float4 a = lds128(cf + k * 16);                  // (a_2k, a_2k, a_2k+1, a_2k+1)
-                    acc[2 * k][0] = fma2(make_float2(a.x, a.y), x01, acc[2 * k][0]);
-                    acc[2 * k][1] = fma2(make_float2(a.x, a.y), x23, acc[2 * k][1]);
-                    if (2 * k + 1 < FF_MT) {
-                        acc[2 * k + 1][0] = fma2(make_float2(a.z, a.w), x01, acc[2 * k + 1][0]);
-                        acc[2 * k + 1][1] = fma2(make_float2(a.z, a.w), x23, acc[2 * k + 1][1]);
+                    for (int k = 0; k < FF_MP / 2; ++k) {
+                        const float4 a = lds128(cf + k * 16);              // (a_2k, a_2k, a_2k+1, a_2k+1)
+                        acc[2 * k][0] = fma2(make_float2(a.x, a.y), x01, acc[2 * k][0]);
+                        acc[2 * k][1] = fma2(make_float2(a.x, a.y), x23, acc[2 * k][1]);
+                        if (2 * k + 1 < FF_MT) {
+                            acc[2 * k + 1][0] = fma2(make_float2(a.z, a.w), x01, acc[2 * k + 1][0]);
+                            acc[2 * k + 1][1] = fma2(make_float2(a.z, a.w), x23, acc[2 * k + 1][1]);
+                        }
                     }
                 }
+                buf ^= 1;
             }
             // the chunk's accumulators -> A stages: row r, 16-byte piece (m_local*2 + h) XOR (r % 8)
 #pragma unroll
@@ -184,21 +195,26 @@ conv_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedPara
 #pragma unroll
                     for (int ml = 0; ml < 4; ++ml) {
                         const int m = g * 4 + ml;
-                        if (m < FF_MT) {
+                        if (m < FF_MT)
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
                                          ::"r"(rowaddr + ((((uint32_t)(ml * 2 + h)) ^ sw) << 4)), "f"(acc[m][0].x),
                                          "f"(acc[m][0].y), "f"(acc[m][1].x), "f"(acc[m][1].y)
                                          : "memory");
-                            if (STORE_Z && zrow != nullptr && m < p.M)
-                                st4_cs(zrow + (size_t)m * p.I + c * 8,
-                                       make_float4(acc[m][0].x, acc[m][0].y, acc[m][1].x, acc[m][1].y));
-                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[s]);
                     ++step;
                 }
+            }
+            // z goes out after the hand-over: the fence above waits for the thread's outstanding memory
+            // operations, so stores issued before it would put a DRAM round trip into every k-step
+            if (STORE_Z && zrow != nullptr) {
+#pragma unroll
+                for (int m = 0; m < FF_MT; ++m)
+                    if (m < p.M)
+                        st4_cs(zrow + (size_t)m * p.I + c * 8,
+                               make_float4(acc[m][0].x, acc[m][0].y, acc[m][1].x, acc[m][1].y));
             }
         }
         cp_async_wait<0>();
@@ -292,7 +308,8 @@ conv_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedPara
     }
 }
 
-constexpr int ff_stages(int bn) { return bn >= 256 ? 3 : (bn >= 128 ? 4 : 6); }
+constexpr int ff_stages(int bn) { return bn >= 128 ? 3 : (bn >= 64 ? 4 : 5); }
+int ff_bn(int O) { const int bn = pick_bn(O); return bn > 128 ? 128 : bn; }
 
 size_t ff_smem(int bn, int PV, int n_max) {
     return (size_t)ff_stages(bn) * (A_BYTES + bn * 128) + FF_FIFO_BYTES + 256 + (size_t)PV * n_max * (FF_MP * 8 + 4) +
@@ -302,12 +319,10 @@ size_t ff_smem(int bn, int PV, int n_max) {
 struct FusedPlan { int PV, bn, n_tiles, n_chunks, G, tail_k8, n_split, chunks_per_split; int64_t tiles; size_t smem; };
 
 bool plan_fused(const Tables *t, int B, int M, int I, int O, FusedPlan *pl) {
-    static const int off = tune_flag("VCM_FUSED_FWD", 1);
-    if (!off) return false;
     if (B % 16 != 0 || B > TM || M < 1 || M > FF_MT || I % 8 != 0 || O % 32 != 0 || I < 8) return false;
     if (encode_fn() == nullptr) return false;
     pl->PV = TM / B;
-    pl->bn = pick_bn(O);
+    pl->bn = ff_bn(O);
     pl->n_tiles = (int)ceil_div(O, pl->bn);
     pl->n_chunks = I / 8;
     pl->G = (M + 3) / 4;
@@ -379,8 +394,7 @@ int fused_fwd(const Tables *t, const float *x, const float *A, const float *W, c
     switch (pl.bn) {
         case 32: e = launch_fused<32>(z != nullptr, grid, pl.smem, mw, p, st); break;
         case 64: e = launch_fused<64>(z != nullptr, grid, pl.smem, mw, p, st); break;
-        case 128: e = launch_fused<128>(z != nullptr, grid, pl.smem, mw, p, st); break;
-        default: e = launch_fused<256>(z != nullptr, grid, pl.smem, mw, p, st); break;
+        default: e = launch_fused<128>(z != nullptr, grid, pl.smem, mw, p, st); break;
     }
     if (e) return e;
     if (pl.n_split > 1) return splitk_fwd_epilogue(ws, pl.n_split, p.R, O, t->p_out, bias, per_point, res, y_act, out,

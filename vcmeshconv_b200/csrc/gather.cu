@@ -641,35 +641,51 @@ int vcm_edge_weights_bwd(const vcm_tables *h, const float *p_nb, const float *dp
 // a u row is one coalesced 4*MO-byte segment. Fixed-order reductions, no atomics.
 namespace vcm {
 
-constexpr int PG_MAXN = 16;       // neighbours handled per register pass of the dA kernel
+constexpr int PG_MAXN = 8;        // neighbours handled per register pass of the dA kernel
+constexpr int PG_UN = 4;          // neighbours / reverse edges / batch entries whose loads are issued together
 
+// All three kernels are latency-bound (a few MB of data, rows of 4*MO bytes): their loops are written branch-free
+// in groups of PG_UN so that the loads of a whole group are in flight before the first FMA needs one.
 template <int NB>                 // NB = batch entries per warp pass
 __global__ void __launch_bounds__(128)
-project_gather_fwd_kernel(const int32_t *__restrict__ idx, const float *__restrict__ u, const float *__restrict__ A,
-                          float *__restrict__ s, int p_in, int p_out, int n_max, int B, int M, int O) {
+project_gather_fwd_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ last,
+                          const float *__restrict__ u, const float *__restrict__ A, float *__restrict__ s, int p_in,
+                          int p_out, int n_max, int B, int M, int O) {
     __shared__ float red[4][NB][64];
     const int MO = M * O, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int p = blockIdx.x * 4 + w;
     if (p >= p_out) return;
     const int j0 = lane, j1 = lane + 32;
-    const int m0 = j0 / O, m1 = j1 / O;
     const bool v0 = j0 < MO, v1 = j1 < MO;
+    const int m0 = v0 ? j0 / O : 0, m1 = v1 ? j1 / O : 0;
+    const int e0 = v0 ? j0 : 0, e1 = v1 ? j1 : 0;                     // in-range element to load when the lane is idle
+    const int l = __ldg(last + p);
     const int32_t *ip = idx + (size_t)p * n_max;
     const float *Ap = A + (size_t)p * n_max * M;
     for (int b0 = blockIdx.y * NB; b0 < B; b0 += gridDim.y * NB) {
         float a0[NB], a1[NB];
 #pragma unroll
         for (int k = 0; k < NB; ++k) a0[k] = a1[k] = 0.f;
-        for (int n = 0; n < n_max; ++n) {
-            const int q = __ldg(ip + n);
-            if (q == p_in) continue;                                   // warp-uniform
-            const float c0 = v0 ? __ldg(Ap + n * M + m0) : 0.f, c1 = v1 ? __ldg(Ap + n * M + m1) : 0.f;
+        for (int n0 = 0; n0 < l; n0 += PG_UN) {
+            int q[PG_UN];
+            float c0[PG_UN], c1[PG_UN];
 #pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                if (b0 + k < B) {
-                    const float *ur = u + ((size_t)(b0 + k) * p_in + q) * MO;
-                    if (v0) a0[k] = fmaf(c0, __ldg(ur + j0), a0[k]);
-                    if (v1) a1[k] = fmaf(c1, __ldg(ur + j1), a1[k]);
+            for (int t = 0; t < PG_UN; ++t) {
+                const int n = min(n0 + t, l - 1);
+                const int qq = __ldg(ip + n);
+                const bool real = n0 + t < l && qq != p_in;
+                q[t] = real ? qq : 0;
+                c0[t] = real && v0 ? __ldg(Ap + n * M + m0) : 0.f;     // padding / tail: coefficient 0, row 0
+                c1[t] = real && v1 ? __ldg(Ap + n * M + m1) : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < PG_UN; ++t) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    const int bb = min(b0 + k, B - 1);
+                    const float *ur = u + ((size_t)bb * p_in + q[t]) * MO;
+                    a0[k] = fmaf(c0[t], __ldg(ur + e0), a0[k]);
+                    a1[k] = fmaf(c1[t], __ldg(ur + e1), a1[k]);
                 }
             }
         }
@@ -694,34 +710,50 @@ project_gather_fwd_kernel(const int32_t *__restrict__ idx, const float *__restri
 
 // dA: one warp per output vertex, all batch entries, neighbours in register passes of PG_MAXN.
 __global__ void __launch_bounds__(128)
-project_gather_dA_kernel(const int32_t *__restrict__ idx, const float *__restrict__ ds, const float *__restrict__ u,
-                         float *__restrict__ dA, int p_in, int p_out, int n_max, int B, int M, int O) {
+project_gather_dA_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ last,
+                         const float *__restrict__ ds, const float *__restrict__ u, float *__restrict__ dA, int p_in,
+                         int p_out, int n_max, int B, int M, int O) {
     __shared__ float red[4][64];
     const int MO = M * O, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int p = blockIdx.x * 4 + w;
     if (p >= p_out) return;
     const int j0 = lane, j1 = lane + 32;
     const bool v0 = j0 < MO, v1 = j1 < MO;
-    const int o0 = j0 % O, o1 = j1 % O;
+    const int e0 = v0 ? j0 : 0, e1 = v1 ? j1 : 0;
+    const int o0 = e0 % O, o1 = e1 % O;
+    const int l = __ldg(last + p);
     const int32_t *ip = idx + (size_t)p * n_max;
     float *dAp = dA + (size_t)p * n_max * M;
     for (int nb = 0; nb < n_max; nb += PG_MAXN) {
         float a0[PG_MAXN], a1[PG_MAXN];
         int q[PG_MAXN];
+        bool real[PG_MAXN];
 #pragma unroll
         for (int k = 0; k < PG_MAXN; ++k) {
             a0[k] = a1[k] = 0.f;
-            q[k] = nb + k < n_max ? __ldg(ip + nb + k) : p_in;
+            const int qq = nb + k < l ? __ldg(ip + nb + k) : p_in;
+            real[k] = qq != p_in;
+            q[k] = real[k] ? qq : 0;
         }
-        for (int b = 0; b < B; ++b) {
-            const float *dr = ds + ((size_t)b * p_out + p) * O;
-            const float g0 = v0 ? __ldg(dr + o0) : 0.f, g1 = v1 ? __ldg(dr + o1) : 0.f;
+        if (nb < l) {
+            for (int b0 = 0; b0 < B; b0 += PG_UN) {
+                float g0[PG_UN], g1[PG_UN];
 #pragma unroll
-            for (int k = 0; k < PG_MAXN; ++k) {
-                if (q[k] != p_in) {                                    // warp-uniform
-                    const float *ur = u + ((size_t)b * p_in + q[k]) * MO;
-                    if (v0) a0[k] = fmaf(g0, __ldg(ur + j0), a0[k]);
-                    if (v1) a1[k] = fmaf(g1, __ldg(ur + j1), a1[k]);
+                for (int t = 0; t < PG_UN; ++t) {
+                    const bool in = b0 + t < B;
+                    const float *dr = ds + ((size_t)min(b0 + t, B - 1) * p_out + p) * O;
+                    g0[t] = in && v0 ? __ldg(dr + o0) : 0.f;             // idle lanes and the batch tail add exact zeros
+                    g1[t] = in && v1 ? __ldg(dr + o1) : 0.f;
+                }
+#pragma unroll
+                for (int t = 0; t < PG_UN; ++t) {
+                    const float *ub = u + (size_t)min(b0 + t, B - 1) * p_in * MO;
+#pragma unroll
+                    for (int k = 0; k < PG_MAXN; ++k) {
+                        const float *ur = ub + (size_t)q[k] * MO;
+                        a0[k] = fmaf(g0[t], __ldg(ur + e0), a0[k]);
+                        a1[k] = fmaf(g1[t], __ldg(ur + e1), a1[k]);
+                    }
                 }
             }
         }
@@ -733,7 +765,7 @@ project_gather_dA_kernel(const int32_t *__restrict__ idx, const float *__restric
             __syncwarp();
             if (lane < M) {
                 float t = 0.f;
-                if (q[k] != p_in)
+                if (real[k])
                     for (int o = 0; o < O; ++o) t += red[w][lane * O + o];
                 dAp[(size_t)(nb + k) * M + lane] = t;                   // padding slots: exactly 0
             }
@@ -753,22 +785,31 @@ project_gather_du_kernel(const int32_t *__restrict__ rev_ptr, const int32_t *__r
     if (q >= p_in) return;
     const int j0 = lane, j1 = lane + 32;
     const bool v0 = j0 < MO, v1 = j1 < MO;
-    const int m0 = j0 / O, m1 = j1 / O, o0 = j0 % O, o1 = j1 % O;
+    const int x0 = v0 ? j0 : 0, x1 = v1 ? j1 : 0;
+    const int m0 = x0 / O, m1 = x1 / O, o0 = x0 % O, o1 = x1 % O;
     const int e0 = __ldg(rev_ptr + q), e1 = __ldg(rev_ptr + q + 1);
     for (int b0 = blockIdx.y * NB; b0 < B; b0 += gridDim.y * NB) {
         float a0[NB], a1[NB];
 #pragma unroll
         for (int k = 0; k < NB; ++k) a0[k] = a1[k] = 0.f;
-        for (int e = e0; e < e1; ++e) {
-            const int slot = __ldg(rev_slot + e);
-            const int p = slot / n_max;
-            const float c0 = v0 ? __ldg(A + (size_t)slot * M + m0) : 0.f, c1 = v1 ? __ldg(A + (size_t)slot * M + m1) : 0.f;
+        for (int e = e0; e < e1; e += PG_UN) {
+            int pp[PG_UN];
+            float c0[PG_UN], c1[PG_UN];
 #pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                if (b0 + k < B) {
-                    const float *dr = ds + ((size_t)(b0 + k) * p_out + p) * O;
-                    if (v0) a0[k] = fmaf(c0, __ldg(dr + o0), a0[k]);
-                    if (v1) a1[k] = fmaf(c1, __ldg(dr + o1), a1[k]);
+            for (int t = 0; t < PG_UN; ++t) {
+                const bool in = e + t < e1;
+                const int slot = __ldg(rev_slot + min(e + t, e1 - 1));
+                pp[t] = slot / n_max;
+                c0[t] = in && v0 ? __ldg(A + (size_t)slot * M + m0) : 0.f;
+                c1[t] = in && v1 ? __ldg(A + (size_t)slot * M + m1) : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < PG_UN; ++t) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    const float *dr = ds + ((size_t)min(b0 + k, B - 1) * p_out + pp[t]) * O;
+                    a0[k] = fmaf(c0[t], __ldg(dr + o0), a0[k]);
+                    a1[k] = fmaf(c1[t], __ldg(dr + o1), a1[k]);
                 }
             }
         }
@@ -795,8 +836,8 @@ int vcm_project_gather_fwd(const vcm_tables *h, const float *u, const float *A, 
     VCM_DEVPTR(u); VCM_DEVPTR(A); VCM_DEVPTR(s);
     if (t->p_out == 0) return VCM_OK;
     dim3 grid((unsigned)ceil_div(t->p_out, 4), (unsigned)ceil_div(B, 4));
-    project_gather_fwd_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(t->idx, u, A, s, t->p_in, t->p_out, t->n_max, B,
-                                                                         M, O);
+    project_gather_fwd_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(t->idx, t->last, u, A, s, t->p_in, t->p_out,
+                                                                         t->n_max, B, M, O);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
@@ -810,8 +851,8 @@ int vcm_project_gather_bwd(const vcm_tables *h, const float *ds, const float *u,
     cudaStream_t st = (cudaStream_t)stream;
     if (dA != nullptr && t->p_out > 0) {
         VCM_CHECK(u != nullptr, "u is required for dA");
-        project_gather_dA_kernel<<<(unsigned)ceil_div(t->p_out, 4), 128, 0, st>>>(t->idx, ds, u, dA, t->p_in, t->p_out,
-                                                                                  t->n_max, B, M, O);
+        project_gather_dA_kernel<<<(unsigned)ceil_div(t->p_out, 4), 128, 0, st>>>(t->idx, t->last, ds, u, dA, t->p_in,
+                                                                                  t->p_out, t->n_max, B, M, O);
         VCM_LAUNCH_CHECK();
     }
     if (du != nullptr && t->p_in > 0) {

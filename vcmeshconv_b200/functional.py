@@ -416,6 +416,11 @@ def basis_gemm(z, weights, bias, res, M, I, O, act, scale_y=1.0, scale_res=0.0, 
                             _precision if precision is None else precision)
 
 
+# Opt-in (VCM_FUSED_FWD=1): on the C2 training step the fused kernel is still slower than K1 + K2 (its CUDA-core
+# producer runs at one CTA per SM); see DESIGN.md section 7. The C entry point itself is always available.
+fused_conv_enabled = __import__("os").environ.get("VCM_FUSED_FWD", "0") == "1"
+
+
 def fused_conv_supported(tables, B, M, I, O, precision=None):
     prec = _precision if precision is None else precision
     return bool(_lib.lib().vcm_conv_fwd_fused_supported(tables.handle, B, M, I, O, prec))
