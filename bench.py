@@ -33,8 +33,13 @@ BATCH = 16
 N_LEVELS = 7
 RESIDUAL = 0.9
 METRIC = "training meshes/sec (fwd+bwd) D-FAUST AE"
-WORKLOAD = "C2: D-FAUST-shaped AE, 6890-vertex sphere template, 6+6 layers [3,32,64,128,256,512,64], M=17, " \
-           "residual 0.9, batch 16 per GPU"
+
+
+def workload(args):
+    tag = {(6890, 16): "C2: D-FAUST-shaped AE", (150000, 8): "C4-sized AE (150k vertices)",
+           (5023, 64): "C3-sized AE (FLAME-like)"}.get((args.vertices, args.batch), "AE")
+    return "%s, %d-vertex sphere template, 6+6 layers [3,32,64,128,256,512,64], M=17, residual 0.9, batch %d per GPU" % (
+        tag, args.vertices, args.batch)
 
 
 def parse():
@@ -162,7 +167,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "meshes/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": args.batch, "vertices": args.vertices,
+        "config": {"workload": workload(args), "global_batch": args.batch, "vertices": args.vertices,
                    "note": "CPU restatement of the reference (oracle/vcconv_oracle.py, same ATen op sequence as "
                            "graphVAESSW.py:97-163); the Python reference itself cannot travel to the GPU box"},
         "cpu_baseline": {"value": value, "unit": "meshes/s", "cores": cores, "kind": "port", "sample": sample},
@@ -313,7 +318,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": "f32" if precision == "fp32" else "tf32 multiply, f32 storage and accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": gbatch, "vertices": args.vertices,
+            "config": {"workload": workload(args), "global_batch": gbatch, "vertices": args.vertices,
                        "parallelism": "dp%d" % world, "gemm_precision": precision,
                        "launch": "eager" if args.no_graph else "cuda-graph replay of the whole step", "trainable_params": n_params,
                        "point_nums": nums, "l2": "inputs rotate over %d batches; each step streams GBs of "

@@ -1023,18 +1023,45 @@ __device__ __forceinline__ void mma_x(float (&d)[4], const uint32_t (&a)[4], con
     }
 }
 
+constexpr int kTC = 32;            // columns (b, i) per staged tile
+constexpr int kTS = kTC + 4;       // smem row stride in words: (stride / 4) odd -> ldmatrix rows hit disjoint bank groups
+constexpr int kDzRows = 24;        // bases padded to three 8-wide MMA tiles
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t &r0, uint32_t &r1, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// One CTA = one output vertex (blockIdx.x, processing order) x one share of its columns (blockIdx.y); each of the
+// four warps walks its own 32-column tiles. Per tile the warp stages dz[17][32] and the l gathered x rows [l][32]
+// in shared memory with cp.async (16-byte pieces, double buffered: the next tile is in flight while this one is
+// multiplied), then
+//   dA[n][m] += X[n][c] * dz[m][c]^T   M = neighbours, N = bases, K = columns: both operands are k-contiguous in
+//                                      the staged tiles, so every fragment is one ldmatrix (a tf32 = two b16);
+//   dG[n][c]  = A_p[n][m] * dz[m][c]   M = neighbours, N = columns, K = bases: coefficient fragments by ldmatrix
+//                                      (kept in registers for <= 32 neighbours), dz fragments by scalar LDS.
+// dA accumulates in MMA fragments over all tiles of the warp: no per-neighbour lane reduction at all.
 template <int NT16, bool X3, bool HAS_DA, bool HAS_DG>
-__global__ void __launch_bounds__(128, NT16 <= 2 ? 4 : 3)
+__global__ void __launch_bounds__(128, NT16 <= 2 ? 4 : 2)
 coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
                       const float *__restrict__ dz, const float *__restrict__ x, const float *__restrict__ A,
                       float *__restrict__ dA_out, float *__restrict__ dG, int p_in, int p_out, int n_max, int I, int M,
                       int B, int tiles_per_cta) {
     constexpr int NP = NT16 * 16;                                    // padded neighbour count
+    constexpr bool KEEP = NT16 <= 2;                                 // coefficient fragments live in registers
+    constexpr int WARP_WORDS = 2 * (kDzRows + NP) * kTS;            // two buffers of (dz tile + x tile)
     extern __shared__ __align__(16) float smem[];
     float *A_s = smem;                                               // [NP][kK5S]  coefficients (hi = as is)
     float *Al_s = A_s + NP * kK5S;                                   // [NP][kK5S]  lo parts (X3)
     int32_t *idx_s = reinterpret_cast<int32_t *>(Al_s + NP * kK5S);  // [NP], -1 = no neighbour
-    float *part_s = reinterpret_cast<float *>(idx_s + NP);           // [4 warps][NP][24] (reuses nothing: small)
+    float *stage_s = reinterpret_cast<float *>(idx_s + NP);          // [4 warps][WARP_WORDS]; reused as part_s at the end
+    float *part_s = stage_s;                                         // [4 warps][NP][24]
 
     const int slot = blockIdx.x;
     const int2 meta = __ldg(meta_sorted + slot);
@@ -1050,87 +1077,123 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
         const int q = n < l ? __ldg(idx_sorted + (size_t)slot * n_max + n) : p_in;
         idx_s[n] = q == p_in ? -1 : q;
     }
+    for (int e = tid; e < 4 * WARP_WORDS; e += 128) stage_s[e] = 0.f;   // padding rows / columns stay zero
     __syncthreads();
 
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int tiles_per_b = I >> 4, n_tiles = B * tiles_per_b;
+    const int tiles_per_b = I / kTC, n_tiles = B * tiles_per_b;
     const int tile_end = min(n_tiles, (int)(blockIdx.y + 1) * tiles_per_cta);
+    float *my = stage_s + (size_t)warp * WARP_WORDS;
+    const uint32_t my_u = (uint32_t)__cvta_generic_to_shared(my);
+    const uint32_t A_u = (uint32_t)__cvta_generic_to_shared(A_s), Al_u = (uint32_t)__cvta_generic_to_shared(Al_s);
+    constexpr uint32_t BUF_BYTES = (kDzRows + NP) * kTS * 4, X_OFF = kDzRows * kTS * 4;
+
+    // This lane's sixteen-byte pieces of a tile are the same for every tile: dz piece e = lane + 32k is row e/8,
+    // columns 4*(e%8); x piece likewise with the row's neighbour id. Offsets are computed once.
+    constexpr int DZ_P = (kDzRows * (kTC / 4) + 31) / 32;            // 6 rounds cover up to 24 bases
+    constexpr int X_P = 2;                                           // x rounds kept in registers (l <= 8); rest looped
+    int dz_src[DZ_P], x_src[X_P];
+    uint32_t dz_dst[DZ_P], x_dst[X_P];
+#pragma unroll
+    for (int k = 0; k < DZ_P; ++k) {
+        const int e = lane + 32 * k, m = e >> 3, j = e & 7;
+        dz_src[k] = m < M ? m * I + 4 * j : -1;
+        dz_dst[k] = (uint32_t)(m * kTS + 4 * j) * 4u;
+    }
+#pragma unroll
+    for (int k = 0; k < X_P; ++k) {
+        const int e = lane + 32 * k, n = e >> 3, j = e & 7;
+        const int q = (HAS_DA && n < l) ? idx_s[n] : -1;
+        x_src[k] = q >= 0 ? q * I + 4 * j : -1;
+        x_dst[k] = X_OFF + (uint32_t)(n * kTS + 4 * j) * 4u;
+    }
+    auto stage = [&](int b, int i0, int buf) {
+        const float *dzp = dz + (((size_t)b * p_out + p) * M) * I + i0;
+        const float *xp = x + (size_t)b * p_in * I + i0;
+        const uint32_t base = my_u + (uint32_t)buf * BUF_BYTES;
+#pragma unroll
+        for (int k = 0; k < DZ_P; ++k)
+            if (dz_src[k] >= 0) cp_async_16(base + dz_dst[k], dzp + dz_src[k]);
+        if (HAS_DA) {
+#pragma unroll
+            for (int k = 0; k < X_P; ++k)
+                if (x_src[k] >= 0) cp_async_16(base + x_dst[k], xp + x_src[k]);
+            for (int e = lane + 32 * X_P; e < l * (kTC / 4); e += 32) {
+                const int n = e >> 3, j = e & 7;
+                const int q = idx_s[n];
+                if (q >= 0) cp_async_16(base + X_OFF + (uint32_t)(n * kTS + 4 * j) * 4u, xp + (size_t)q * I + 4 * j);
+            }
+        }
+    };
+    // dG rows this lane stores (bit nt*2: row nt*16+g, bit nt*2+1: row nt*16+g+8): real neighbours only
+    uint32_t st_mask = 0;
+#pragma unroll
+    for (int nt = 0; nt < NT16; ++nt) {
+        const int n0 = nt * 16 + g, n1 = n0 + 8;
+        if (n0 < l && idx_s[n0] >= 0) st_mask |= 1u << (2 * nt);
+        if (n1 < l && idx_s[n1] >= 0) st_mask |= 2u << (2 * nt);
+    }
+
     float acc[NT16][3][4];
 #pragma unroll
     for (int a = 0; a < NT16; ++a)
 #pragma unroll
         for (int b2 = 0; b2 < 3; ++b2) acc[a][b2][0] = acc[a][b2][1] = acc[a][b2][2] = acc[a][b2][3] = 0.f;
 
-    for (int ct = blockIdx.y * tiles_per_cta + warp; ct < tile_end; ct += 4) {
-        const int b = ct / tiles_per_b, i0 = (ct - b * tiles_per_b) << 4;
-        const float *dzp = dz + (((size_t)b * p_out + p) * M) * I + i0;        // [m][16 columns], row stride I
-        if (HAS_DG) {
-            // dz as the A operand (row = column c, col = basis m), three k-steps of 8 bases
-            uint32_t zA[3][4], zAl[3][4];
+    // ldmatrix row addresses of this lane. Operand A (16 x 8): matrices (rows 0-7 | 8-15) x (k 0-3 | 4-7) in the
+    // order a0..a3; operand B (8 x 8 as [n][k]): matrices k 0-3, k 4-7 (x4: two n-tiles).
+    const int lr = lane & 7, lj = lane >> 3;
+    const uint32_t a_row_off = (uint32_t)(((lj & 1) * 8 + lr) * kTS + (lj >> 1) * 4) * 4u;       // X tile, + nt*16 rows, + k
+    const uint32_t b_row_off = (uint32_t)(((lj >> 1) * 8 + lr) * kTS + (lj & 1) * 4) * 4u;       // dz tile, + mt*8 rows, + k
+    const uint32_t c_row_off = (uint32_t)(((lj & 1) * 8 + lr) * kK5S + (lj >> 1) * 4) * 4u;      // coefficient tile
+
+    uint32_t cA[KEEP ? NT16 : 1][3][4], cAl[KEEP ? NT16 : 1][3][4];
+    if (HAS_DG && KEEP) {
+#pragma unroll
+        for (int nt = 0; nt < NT16; ++nt)
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks) {
-                const int m_lo = ks * 8 + t, m_hi = m_lo + 4;
-                zA[ks][0] = m_lo < M ? __float_as_uint(__ldg(dzp + (size_t)m_lo * I + g)) : 0u;
-                zA[ks][1] = m_lo < M ? __float_as_uint(__ldg(dzp + (size_t)m_lo * I + g + 8)) : 0u;
-                zA[ks][2] = m_hi < M ? __float_as_uint(__ldg(dzp + (size_t)m_hi * I + g)) : 0u;
-                zA[ks][3] = m_hi < M ? __float_as_uint(__ldg(dzp + (size_t)m_hi * I + g + 8)) : 0u;
+                ldsm_x4(cA[nt][ks], A_u + c_row_off + (uint32_t)(nt * 16 * kK5S + ks * 8) * 4u);
+                if (X3) ldsm_x4(cAl[nt][ks], Al_u + c_row_off + (uint32_t)(nt * 16 * kK5S + ks * 8) * 4u);
+            }
+    }
+
+    int ct = blockIdx.y * tiles_per_cta + warp;
+    int buf = 0;
+    int b = ct / tiles_per_b, it = ct - b * tiles_per_b;             // tile -> (batch entry, 32-column block)
+    int nb = b, nit = it;                                            // the tile being prefetched
+    if (ct < tile_end) stage(b, it * kTC, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (; ct < tile_end; ct += 4, buf ^= 1) {
+        nit += 4;
+        while (nit >= tiles_per_b) { nit -= tiles_per_b; ++nb; }
+        if (ct + 4 < tile_end) stage(nb, nit * kTC, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t dz_u = my_u + (uint32_t)buf * BUF_BYTES, x_u = dz_u + X_OFF;
+        const float *dz_t = my + (size_t)buf * (BUF_BYTES / 4);
+        const int i0 = it * kTC;
+
+        if (HAS_DA) {
+#pragma unroll
+            for (int kc = 0; kc < kTC / 8; ++kc) {
+                uint32_t zB[3][2], zBl[3][2];
+                {
+                    uint32_t r[4];
+                    ldsm_x4(r, dz_u + b_row_off + (uint32_t)(kc * 8) * 4u);                  // bases 0-7, 8-15
+                    zB[0][0] = r[0]; zB[0][1] = r[1]; zB[1][0] = r[2]; zB[1][1] = r[3];
+                    ldsm_x2(zB[2][0], zB[2][1], dz_u + b_row_off + (uint32_t)(16 * kTS + kc * 8) * 4u);   // bases 16-23
+                }
                 if (X3) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) zAl[ks][r] = tf32_lo(zA[ks][r]);
-                }
-            }
-            float *dGp = dG + (((size_t)b * p_out + p) * n_max) * I + i0 + g;
-#pragma unroll
-            for (int nt = 0; nt < 2 * NT16; ++nt) {
-                if (nt * 8 >= l) break;                                        // warp-uniform
-                float d[4] = {0.f, 0.f, 0.f, 0.f};
-                const float *Ar = A_s + (nt * 8 + g) * kK5S + t, *Alr = Al_s + (nt * 8 + g) * kK5S + t;
-#pragma unroll
-                for (int ks = 0; ks < 3; ++ks)
-                    mma_x<X3>(d, zA[ks], zAl[ks], __float_as_uint(Ar[ks * 8]), __float_as_uint(Ar[ks * 8 + 4]),
-                              __float_as_uint(Alr[ks * 8]), __float_as_uint(Alr[ks * 8 + 4]));
-                const int n0 = nt * 8 + 2 * t;
-                if (n0 < l && idx_s[n0] >= 0) {
-                    dGp[(size_t)n0 * I] = d[0];
-                    dGp[(size_t)n0 * I + 8] = d[2];
-                }
-                if (n0 + 1 < l && idx_s[n0 + 1] >= 0) {
-                    dGp[(size_t)(n0 + 1) * I] = d[1];
-                    dGp[(size_t)(n0 + 1) * I + 8] = d[3];
-                }
-            }
-        }
-        if (HAS_DA) {
-            const float *xb = x + (size_t)b * p_in * I + i0 + t;
-#pragma unroll
-            for (int kc = 0; kc < 2; ++kc) {                                   // two k-steps of 8 columns
-                // dz as the B operand (k = column, n = basis)
-                uint32_t zB[3][2], zBl[3][2];
-#pragma unroll
-                for (int mt = 0; mt < 3; ++mt) {
-                    const int m = mt * 8 + g;
-                    zB[mt][0] = m < M ? __float_as_uint(__ldg(dzp + (size_t)m * I + kc * 8 + t)) : 0u;
-                    zB[mt][1] = m < M ? __float_as_uint(__ldg(dzp + (size_t)m * I + kc * 8 + t + 4)) : 0u;
-                    if (X3) {
-                        zBl[mt][0] = tf32_lo(zB[mt][0]);
-                        zBl[mt][1] = tf32_lo(zB[mt][1]);
-                    }
+                    for (int mt = 0; mt < 3; ++mt) { zBl[mt][0] = tf32_lo(zB[mt][0]); zBl[mt][1] = tf32_lo(zB[mt][1]); }
                 }
 #pragma unroll
                 for (int nt = 0; nt < NT16; ++nt) {
-                    if (nt * 16 >= l) break;                                   // warp-uniform
-                    const int q_lo = idx_s[nt * 16 + g], q_hi = idx_s[nt * 16 + g + 8];
-                    uint32_t xa[4] = {0u, 0u, 0u, 0u}, xal[4] = {0u, 0u, 0u, 0u};
-                    if (q_lo >= 0) {
-                        const float *r = xb + (size_t)q_lo * I + kc * 8;
-                        xa[0] = __float_as_uint(__ldg(r));
-                        xa[2] = __float_as_uint(__ldg(r + 4));
-                    }
-                    if (q_hi >= 0) {
-                        const float *r = xb + (size_t)q_hi * I + kc * 8;
-                        xa[1] = __float_as_uint(__ldg(r));
-                        xa[3] = __float_as_uint(__ldg(r + 4));
-                    }
+                    if (NT16 > 1 && nt * 16 >= l) break;                       // warp-uniform
+                    uint32_t xa[4], xal[4] = {0u, 0u, 0u, 0u};
+                    ldsm_x4(xa, x_u + a_row_off + (uint32_t)(nt * 16 * kTS + kc * 8) * 4u);
                     if (X3) {
 #pragma unroll
                         for (int r = 0; r < 4; ++r) xal[r] = tf32_lo(xa[r]);
@@ -1141,10 +1204,48 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                 }
             }
         }
+        if (HAS_DG) {
+            float *dGp = dG + (((size_t)b * p_out + p) * n_max) * I + i0 + 2 * t;
+#pragma unroll
+            for (int c8 = 0; c8 < kTC / 8; ++c8) {
+                // dz as the B operand: k = basis, n = column
+                uint32_t zb[3][2], zbl[3][2];
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                    zb[ks][0] = __float_as_uint(dz_t[(ks * 8 + t) * kTS + c8 * 8 + g]);
+                    zb[ks][1] = __float_as_uint(dz_t[(ks * 8 + t + 4) * kTS + c8 * 8 + g]);
+                    if (X3) { zbl[ks][0] = tf32_lo(zb[ks][0]); zbl[ks][1] = tf32_lo(zb[ks][1]); }
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT16; ++nt) {
+                    if (NT16 > 1 && nt * 16 >= l) break;                       // warp-uniform
+                    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        if (KEEP) {
+                            mma_x<X3>(d, cA[nt][ks], cAl[nt][ks], zb[ks][0], zb[ks][1], zbl[ks][0], zbl[ks][1]);
+                        } else {
+                            uint32_t ca[4], cal[4] = {0u, 0u, 0u, 0u};
+                            ldsm_x4(ca, A_u + c_row_off + (uint32_t)(nt * 16 * kK5S + ks * 8) * 4u);
+                            if (X3) ldsm_x4(cal, Al_u + c_row_off + (uint32_t)(nt * 16 * kK5S + ks * 8) * 4u);
+                            mma_x<X3>(d, ca, cal, zb[ks][0], zb[ks][1], zbl[ks][0], zbl[ks][1]);
+                        }
+                    }
+                    float *row0 = dGp + (size_t)(nt * 16 + g) * I + c8 * 8;
+                    if (st_mask & (1u << (2 * nt))) *reinterpret_cast<float2 *>(row0) = make_float2(d[0], d[1]);
+                    if (st_mask & (2u << (2 * nt))) *reinterpret_cast<float2 *>(row0 + (size_t)8 * I) = make_float2(d[2], d[3]);
+                }
+            }
+        }
+        __syncwarp();                                  // every lane is done with this buffer before it is refilled
+        b = nb;
+        it = nit;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (!HAS_DA) return;
 
-    // fragments -> smem, then a fixed-order sum over the four warps; padding slots get exactly 0
+    // fragments -> smem (the staging area is free now), then a fixed-order sum over the four warps
+    __syncthreads();
     float *pw = part_s + (size_t)warp * NP * 24;
 #pragma unroll
     for (int nt = 0; nt < NT16; ++nt)
@@ -1170,9 +1271,9 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
 struct MmaGradPlan { int nt16, gy, tiles_per_cta; size_t smem; };
 
 static bool plan_grad_mma(const Tables *t, int B, int I, int M, MmaGradPlan *pl) {
-    if (M > 24 || M < 2 || (I & 15) != 0 || t->n_max > 64 || t->p_out == 0) return false;
+    if (M > 24 || M < 2 || I % kTC != 0 || t->n_max > 64 || t->p_out == 0) return false;
     pl->nt16 = (t->n_max + 15) / 16;
-    const int n_tiles = B * (I >> 4);
+    const int n_tiles = B * (I / kTC);
     int64_t want = ceil_div(8 * (int64_t)sm_count(), t->p_out);        // ~8 CTAs of 4 warps per SM overall
     if (want < 1) want = 1;
     const int64_t max_gy = ceil_div(n_tiles, 8);                       // at least two tiles per warp
@@ -1181,7 +1282,7 @@ static bool plan_grad_mma(const Tables *t, int B, int I, int M, MmaGradPlan *pl)
     pl->tiles_per_cta = (int)(ceil_div(ceil_div(n_tiles, gy), 4) * 4);
     pl->gy = (int)ceil_div(n_tiles, pl->tiles_per_cta);
     const int NP = pl->nt16 * 16;
-    pl->smem = ((size_t)2 * NP * kK5S + NP + (size_t)4 * NP * 24) * sizeof(float);
+    pl->smem = ((size_t)2 * NP * kK5S + NP + (size_t)4 * 2 * (kDzRows + NP) * kTS) * sizeof(float);
     return true;
 }
 
