@@ -136,4 +136,5 @@ def test_fused_autograd_matches_two_kernel_path():
     g2 = torch.autograd.grad(o2, (x, A, W, bias, res), dout)
     assert rel_err(o1, o2) < EXACT_TOL
     for a, b in zip(g1, g2):
-        assert rel_err(a, b) < 1e-4          # ELU' switches on out, which differs by accumulation order
+        # out differs by accumulation order; downstream of it dz, dA and dx go through TF32 products again
+        assert rel_err(a, b) < TF32_TOL

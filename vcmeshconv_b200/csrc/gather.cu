@@ -1038,15 +1038,18 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+constexpr int kNBuf = 3;           // staged tiles per warp: two in flight while one is multiplied
+
 // One CTA = one output vertex (blockIdx.x, processing order) x one share of its columns (blockIdx.y); each of the
-// four warps walks its own 32-column tiles. Per tile the warp stages dz[17][32] and the l gathered x rows [l][32]
-// in shared memory with cp.async (16-byte pieces, double buffered: the next tile is in flight while this one is
-// multiplied), then
+// four warps walks its own 32-column tiles. Per tile the warp stages dz[M][32] and the gathered x rows [n_max][32]
+// in shared memory with cp.async (16-byte pieces, three buffers: two tiles are in flight while one is multiplied),
+// then
 //   dA[n][m] += X[n][c] * dz[m][c]^T   M = neighbours, N = bases, K = columns: both operands are k-contiguous in
 //                                      the staged tiles, so every fragment is one ldmatrix (a tf32 = two b16);
 //   dG[n][c]  = A_p[n][m] * dz[m][c]   M = neighbours, N = columns, K = bases: coefficient fragments by ldmatrix
 //                                      (kept in registers for <= 32 neighbours), dz fragments by scalar LDS.
-// dA accumulates in MMA fragments over all tiles of the warp: no per-neighbour lane reduction at all.
+// dA accumulates in MMA fragments over all tiles of the warp: no per-neighbour lane reduction at all. Rows that do
+// not exist (bases >= M, padding neighbours) are not staged: their ldmatrix / LDS addresses point at one zero row.
 template <int NT16, bool X3, bool HAS_DA, bool HAS_DG>
 __global__ void __launch_bounds__(128, NT16 <= 2 ? 4 : 2)
 coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
@@ -1055,76 +1058,98 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                       int B, int tiles_per_cta) {
     constexpr int NP = NT16 * 16;                                    // padded neighbour count
     constexpr bool KEEP = NT16 <= 2;                                 // coefficient fragments live in registers
-    constexpr int WARP_WORDS = 2 * (kDzRows + NP) * kTS;            // two buffers of (dz tile + x tile)
     extern __shared__ __align__(16) float smem[];
     float *A_s = smem;                                               // [NP][kK5S]  coefficients (hi = as is)
-    float *Al_s = A_s + NP * kK5S;                                   // [NP][kK5S]  lo parts (X3)
-    int32_t *idx_s = reinterpret_cast<int32_t *>(Al_s + NP * kK5S);  // [NP], -1 = no neighbour
-    float *stage_s = reinterpret_cast<float *>(idx_s + NP);          // [4 warps][WARP_WORDS]; reused as part_s at the end
+    float *Al_s = A_s + NP * kK5S;                                   // [NP][kK5S]  lo parts (X3 only)
+    int32_t *idx_s = reinterpret_cast<int32_t *>(Al_s + (X3 ? NP * kK5S : 0));   // [NP], -1 = no neighbour
+    float *zero_s = reinterpret_cast<float *>(idx_s + NP);           // [kTS] zeros
+    float *stage_s = zero_s + kTS;                                   // [4 warps][kNBuf][M + n_max][kTS]; part_s at the end
     float *part_s = stage_s;                                         // [4 warps][NP][24]
+    const int buf_words = (M + n_max) * kTS, warp_words = kNBuf * buf_words;
 
     const int slot = blockIdx.x;
     const int2 meta = __ldg(meta_sorted + slot);
     const int p = meta.x, l = meta.y;
     const int tid = threadIdx.x;
-    for (int e = tid; e < NP * kK5S; e += 128) {
-        const int n = e / kK5S, m = e - n * kK5S;
-        const float a = (n < l && m < M) ? __ldg(A + ((size_t)p * n_max + n) * M + m) : 0.f;
-        A_s[e] = a;
-        Al_s[e] = __uint_as_float(tf32_lo(__float_as_uint(a)));
-    }
-    for (int n = tid; n < NP; n += 128) {
-        const int q = n < l ? __ldg(idx_sorted + (size_t)slot * n_max + n) : p_in;
-        idx_s[n] = q == p_in ? -1 : q;
-    }
-    for (int e = tid; e < 4 * WARP_WORDS; e += 128) stage_s[e] = 0.f;   // padding rows / columns stay zero
-    __syncthreads();
-
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int tiles_per_b = I / kTC, n_tiles = B * tiles_per_b;
     const int tile_end = min(n_tiles, (int)(blockIdx.y + 1) * tiles_per_cta);
-    float *my = stage_s + (size_t)warp * WARP_WORDS;
+    float *my = stage_s + (size_t)warp * warp_words;
     const uint32_t my_u = (uint32_t)__cvta_generic_to_shared(my);
-    const uint32_t A_u = (uint32_t)__cvta_generic_to_shared(A_s), Al_u = (uint32_t)__cvta_generic_to_shared(Al_s);
-    constexpr uint32_t BUF_BYTES = (kDzRows + NP) * kTS * 4, X_OFF = kDzRows * kTS * 4;
+    const uint32_t zero_u = (uint32_t)__cvta_generic_to_shared(zero_s);
+    const uint32_t buf_bytes = (uint32_t)buf_words * 4u, x_off = (uint32_t)(M * kTS) * 4u;
 
     // This lane's sixteen-byte pieces of a tile are the same for every tile: dz piece e = lane + 32k is row e/8,
-    // columns 4*(e%8); x piece likewise with the row's neighbour id. Offsets are computed once.
-    constexpr int DZ_P = (kDzRows * (kTC / 4) + 31) / 32;            // 6 rounds cover up to 24 bases
-    constexpr int X_P = 2;                                           // x rounds kept in registers (l <= 8); rest looped
-    int dz_src[DZ_P], x_src[X_P];
-    uint32_t dz_dst[DZ_P], x_dst[X_P];
+    // columns 4*(e%8). The dz half of the first tiles is requested before anything else: it needs no table.
+    constexpr int DZ_P = (24 * (kTC / 4) + 31) / 32;                // 6 rounds cover up to 24 bases
+    int dz_src[DZ_P];
+    uint32_t dz_dst[DZ_P];
 #pragma unroll
     for (int k = 0; k < DZ_P; ++k) {
         const int e = lane + 32 * k, m = e >> 3, j = e & 7;
         dz_src[k] = m < M ? m * I + 4 * j : -1;
         dz_dst[k] = (uint32_t)(m * kTS + 4 * j) * 4u;
     }
+    auto stage_dz = [&](int b, int i0, int buf) {
+        const float *dzp = dz + (((size_t)b * p_out + p) * M) * I + i0;
+        const uint32_t base = my_u + (uint32_t)buf * buf_bytes;
+#pragma unroll
+        for (int k = 0; k < DZ_P; ++k)
+            if (dz_src[k] >= 0) cp_async_16(base + dz_dst[k], dzp + dz_src[k]);
+    };
+    int ct = blockIdx.y * tiles_per_cta + warp;
+    int b = ct / tiles_per_b, it = ct - b * tiles_per_b;             // tile -> (batch entry, 32-column block)
+    int nb = b, nit = it;                                            // cursor of the tile being prefetched
+    auto advance = [&]() {
+        nit += 4;
+        while (nit >= tiles_per_b) { nit -= tiles_per_b; ++nb; }
+    };
+    if (ct < tile_end) stage_dz(b, it * kTC, 0);
+    int b1 = 0, it1 = 0;
+    if (ct + 4 < tile_end) { advance(); b1 = nb; it1 = nit; stage_dz(nb, nit * kTC, 1); }
+
+    for (int e = tid; e < NP * kK5S; e += 128) {
+        const int n = e / kK5S, m = e - n * kK5S;
+        const float a = (n < l && m < M) ? __ldg(A + ((size_t)p * n_max + n) * M + m) : 0.f;
+        A_s[e] = a;
+        if (X3) Al_s[e] = __uint_as_float(tf32_lo(__float_as_uint(a)));
+    }
+    for (int n = tid; n < NP; n += 128) {
+        const int q = n < l ? __ldg(idx_sorted + (size_t)slot * n_max + n) : p_in;
+        idx_s[n] = q == p_in ? -1 : q;
+    }
+    if (tid < kTS) zero_s[tid] = 0.f;
+    __syncthreads();
+
+    // x pieces of this lane (rounds beyond the first two are looped), then the x half of the first tiles
+    constexpr int X_P = 2;
+    int x_src[X_P];
+    uint32_t x_dst[X_P];
 #pragma unroll
     for (int k = 0; k < X_P; ++k) {
         const int e = lane + 32 * k, n = e >> 3, j = e & 7;
         const int q = (HAS_DA && n < l) ? idx_s[n] : -1;
         x_src[k] = q >= 0 ? q * I + 4 * j : -1;
-        x_dst[k] = X_OFF + (uint32_t)(n * kTS + 4 * j) * 4u;
+        x_dst[k] = x_off + (uint32_t)(n * kTS + 4 * j) * 4u;
     }
-    auto stage = [&](int b, int i0, int buf) {
-        const float *dzp = dz + (((size_t)b * p_out + p) * M) * I + i0;
+    auto stage_x = [&](int b, int i0, int buf) {
+        if (!HAS_DA) return;
         const float *xp = x + (size_t)b * p_in * I + i0;
-        const uint32_t base = my_u + (uint32_t)buf * BUF_BYTES;
+        const uint32_t base = my_u + (uint32_t)buf * buf_bytes;
 #pragma unroll
-        for (int k = 0; k < DZ_P; ++k)
-            if (dz_src[k] >= 0) cp_async_16(base + dz_dst[k], dzp + dz_src[k]);
-        if (HAS_DA) {
-#pragma unroll
-            for (int k = 0; k < X_P; ++k)
-                if (x_src[k] >= 0) cp_async_16(base + x_dst[k], xp + x_src[k]);
-            for (int e = lane + 32 * X_P; e < l * (kTC / 4); e += 32) {
-                const int n = e >> 3, j = e & 7;
-                const int q = idx_s[n];
-                if (q >= 0) cp_async_16(base + X_OFF + (uint32_t)(n * kTS + 4 * j) * 4u, xp + (size_t)q * I + 4 * j);
-            }
+        for (int k = 0; k < X_P; ++k)
+            if (x_src[k] >= 0) cp_async_16(base + x_dst[k], xp + x_src[k]);
+        for (int e = lane + 32 * X_P; e < l * (kTC / 4); e += 32) {
+            const int n = e >> 3, j = e & 7;
+            const int q = idx_s[n];
+            if (q >= 0) cp_async_16(base + x_off + (uint32_t)(n * kTS + 4 * j) * 4u, xp + (size_t)q * I + 4 * j);
         }
     };
+    if (ct < tile_end) stage_x(b, it * kTC, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (ct + 4 < tile_end) stage_x(b1, it1 * kTC, 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
     // dG rows this lane stores (bit nt*2: row nt*16+g, bit nt*2+1: row nt*16+g+8): real neighbours only
     uint32_t st_mask = 0;
 #pragma unroll
@@ -1140,12 +1165,29 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
 #pragma unroll
         for (int b2 = 0; b2 < 3; ++b2) acc[a][b2][0] = acc[a][b2][1] = acc[a][b2][2] = acc[a][b2][3] = 0.f;
 
-    // ldmatrix row addresses of this lane. Operand A (16 x 8): matrices (rows 0-7 | 8-15) x (k 0-3 | 4-7) in the
-    // order a0..a3; operand B (8 x 8 as [n][k]): matrices k 0-3, k 4-7 (x4: two n-tiles).
+    // ldmatrix row addresses of this lane (byte offsets inside a buffer, or -1 = the zero row). Operand A (16 x 8):
+    // matrices (rows 0-7 | 8-15) x (k 0-3 | 4-7) in the order a0..a3; operand B (8 x 8 as [n][k]): k 0-3, k 4-7.
     const int lr = lane & 7, lj = lane >> 3;
-    const uint32_t a_row_off = (uint32_t)(((lj & 1) * 8 + lr) * kTS + (lj >> 1) * 4) * 4u;       // X tile, + nt*16 rows, + k
-    const uint32_t b_row_off = (uint32_t)(((lj >> 1) * 8 + lr) * kTS + (lj & 1) * 4) * 4u;       // dz tile, + mt*8 rows, + k
+    int a_off[NT16], b4_off, b2_off;
+#pragma unroll
+    for (int nt = 0; nt < NT16; ++nt) {
+        const int n = nt * 16 + (lj & 1) * 8 + lr;
+        a_off[nt] = (n < l && idx_s[n] >= 0) ? (int)x_off + (n * kTS + (lj >> 1) * 4) * 4 : -1;
+    }
+    {
+        const int m4 = (lj >> 1) * 8 + lr, m2 = 16 + lr;
+        b4_off = m4 < M ? (m4 * kTS + (lj & 1) * 4) * 4 : -1;
+        b2_off = m2 < M ? (m2 * kTS + (lj & 1) * 4) * 4 : -1;
+    }
     const uint32_t c_row_off = (uint32_t)(((lj & 1) * 8 + lr) * kK5S + (lj >> 1) * 4) * 4u;      // coefficient tile
+    const uint32_t A_u = (uint32_t)__cvta_generic_to_shared(A_s), Al_u = (uint32_t)__cvta_generic_to_shared(Al_s);
+    // dz rows read by the scalar B-fragment loads of dG: basis ks*8 + t (+4); -1 = zero row
+    int zrow[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const int m = (r >> 1) * 8 + t + (r & 1) * 4;
+        zrow[r] = m < M ? m * kTS + g : -1;
+    }
 
     uint32_t cA[KEEP ? NT16 : 1][3][4], cAl[KEEP ? NT16 : 1][3][4];
     if (HAS_DG && KEEP) {
@@ -1158,21 +1200,18 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
             }
     }
 
-    int ct = blockIdx.y * tiles_per_cta + warp;
-    int buf = 0;
-    int b = ct / tiles_per_b, it = ct - b * tiles_per_b;             // tile -> (batch entry, 32-column block)
-    int nb = b, nit = it;                                            // the tile being prefetched
-    if (ct < tile_end) stage(b, it * kTC, 0);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (; ct < tile_end; ct += 4, buf ^= 1) {
-        nit += 4;
-        while (nit >= tiles_per_b) { nit -= tiles_per_b; ++nb; }
-        if (ct + 4 < tile_end) stage(nb, nit * kTC, buf ^ 1);
+    int buf = 0, pbuf = 2;                                           // buffer being multiplied / being filled
+    for (; ct < tile_end; ct += 4) {
+        if (ct + 8 < tile_end) {
+            advance();
+            stage_dz(nb, nit * kTC, pbuf);
+            stage_x(nb, nit * kTC, pbuf);
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
         __syncwarp();
-        const uint32_t dz_u = my_u + (uint32_t)buf * BUF_BYTES, x_u = dz_u + X_OFF;
-        const float *dz_t = my + (size_t)buf * (BUF_BYTES / 4);
+        const uint32_t dz_u = my_u + (uint32_t)buf * buf_bytes;
+        const float *dz_t = my + (size_t)buf * buf_words;
         const int i0 = it * kTC;
 
         if (HAS_DA) {
@@ -1181,9 +1220,9 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                 uint32_t zB[3][2], zBl[3][2];
                 {
                     uint32_t r[4];
-                    ldsm_x4(r, dz_u + b_row_off + (uint32_t)(kc * 8) * 4u);                  // bases 0-7, 8-15
+                    ldsm_x4(r, b4_off >= 0 ? dz_u + (uint32_t)b4_off + (uint32_t)(kc * 8) * 4u : zero_u);   // bases 0-7, 8-15
                     zB[0][0] = r[0]; zB[0][1] = r[1]; zB[1][0] = r[2]; zB[1][1] = r[3];
-                    ldsm_x2(zB[2][0], zB[2][1], dz_u + b_row_off + (uint32_t)(16 * kTS + kc * 8) * 4u);   // bases 16-23
+                    ldsm_x2(zB[2][0], zB[2][1], b2_off >= 0 ? dz_u + (uint32_t)b2_off + (uint32_t)(kc * 8) * 4u : zero_u);
                 }
                 if (X3) {
 #pragma unroll
@@ -1193,7 +1232,7 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                 for (int nt = 0; nt < NT16; ++nt) {
                     if (NT16 > 1 && nt * 16 >= l) break;                       // warp-uniform
                     uint32_t xa[4], xal[4] = {0u, 0u, 0u, 0u};
-                    ldsm_x4(xa, x_u + a_row_off + (uint32_t)(nt * 16 * kTS + kc * 8) * 4u);
+                    ldsm_x4(xa, a_off[nt] >= 0 ? dz_u + (uint32_t)a_off[nt] + (uint32_t)(kc * 8) * 4u : zero_u);
                     if (X3) {
 #pragma unroll
                         for (int r = 0; r < 4; ++r) xal[r] = tf32_lo(xa[r]);
@@ -1211,10 +1250,10 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                 // dz as the B operand: k = basis, n = column
                 uint32_t zb[3][2], zbl[3][2];
 #pragma unroll
-                for (int ks = 0; ks < 3; ++ks) {
-                    zb[ks][0] = __float_as_uint(dz_t[(ks * 8 + t) * kTS + c8 * 8 + g]);
-                    zb[ks][1] = __float_as_uint(dz_t[(ks * 8 + t + 4) * kTS + c8 * 8 + g]);
-                    if (X3) { zbl[ks][0] = tf32_lo(zb[ks][0]); zbl[ks][1] = tf32_lo(zb[ks][1]); }
+                for (int r = 0; r < 6; ++r) {
+                    const uint32_t v = zrow[r] >= 0 ? __float_as_uint(dz_t[zrow[r] + c8 * 8]) : 0u;
+                    zb[r >> 1][r & 1] = v;
+                    if (X3) zbl[r >> 1][r & 1] = tf32_lo(v);
                 }
 #pragma unroll
                 for (int nt = 0; nt < NT16; ++nt) {
@@ -1238,8 +1277,11 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
             }
         }
         __syncwarp();                                  // every lane is done with this buffer before it is refilled
-        b = nb;
-        it = nit;
+        // the tile just multiplied came from the cursor two steps back: recompute (b, it) of the next one
+        it += 4;
+        while (it >= tiles_per_b) { it -= tiles_per_b; ++b; }
+        pbuf = buf;
+        buf = buf == kNBuf - 1 ? 0 : buf + 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (!HAS_DA) return;
@@ -1282,7 +1324,8 @@ static bool plan_grad_mma(const Tables *t, int B, int I, int M, MmaGradPlan *pl)
     pl->tiles_per_cta = (int)(ceil_div(ceil_div(n_tiles, gy), 4) * 4);
     pl->gy = (int)ceil_div(n_tiles, pl->tiles_per_cta);
     const int NP = pl->nt16 * 16;
-    pl->smem = ((size_t)2 * NP * kK5S + NP + (size_t)4 * 2 * (kDzRows + NP) * kTS) * sizeof(float);
+    size_t stage = (size_t)4 * kNBuf * (M + t->n_max) * kTS, part = (size_t)4 * NP * 24;
+    pl->smem = ((size_t)2 * NP * kK5S + NP + kTS + (stage > part ? stage : part)) * sizeof(float);
     return true;
 }
 
@@ -1326,13 +1369,14 @@ int vcm_coeff_grad_ex(const vcm_tables *h, const float *dz, const float *x, cons
                       float *ws, int B, int I, int M, int precision, void *stream) {
     using namespace vcm;
     const Tables *t = as_tables(h);
-    // opt-in: correct in both modes (the whole parity suite passes with VCM_K5_MMA=1) but measured slower than
-    // the fp32 kernel (unpool3: 264 vs 119 us; step +0.43 ms): fragments taken straight from global memory are
-    // 4-byte, sector-granular accesses (5x the L1 sector requests of the 128-bit strip loads, dz read in two
-    // layouts). A tensor-pipe K5 needs dz / x tiles staged in shared memory first (round-2 item).
-    static const int use_mma = [] { const char *e = getenv("VCM_K5_MMA"); return e ? atoi(e) : 0; }();
+    // Tensor-pipe K5 (shared-memory staged tiles, ldmatrix fragments): in TF32 mode it is the default for layers with
+    // <= 32 neighbours per vertex, where it is 17-27 % faster than the fp32 kernel (C2 step: 3.49 -> 3.38 ms); with
+    // more neighbours (the pooling layers) the coefficient fragments no longer fit in registers and the fp32 kernel
+    // wins. VCM_K5_MMA: 0 = never, 1 = wherever it applies (also in tf32x3 mode), 2 = the default rule.
+    static const int use_mma = [] { const char *e = getenv("VCM_K5_MMA"); return e ? atoi(e) : 2; }();
     MmaGradPlan pl;
-    if (!use_mma || precision == VCM_PREC_FP32 || t == nullptr || B <= 0 || !plan_grad_mma(t, B, I, M, &pl))
+    if (!use_mma || precision == VCM_PREC_FP32 || t == nullptr || B <= 0 || !plan_grad_mma(t, B, I, M, &pl) ||
+        (use_mma >= 2 && (pl.nt16 > 2 || precision != VCM_PREC_TF32)))
         return vcm_coeff_grad(h, dz, x, A, dA, dG, ws, B, I, M, stream);
     VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR_OPT(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
     VCM_CHECK(dA != nullptr || dG != nullptr, "nothing to compute: dA and dG are both NULL");
