@@ -1024,7 +1024,11 @@ __device__ __forceinline__ void mma_x(float (&d)[4], const uint32_t (&a)[4], con
 }
 
 constexpr int kTC = 32;            // columns (b, i) per staged tile
-constexpr int kTS = kTC + 4;       // smem row stride in words: (stride / 4) odd -> ldmatrix rows hit disjoint bank groups
+constexpr int kTS = kTC;           // smem row = 32 words, no padding: the 16-byte chunks of a row are XOR-swizzled
+// chunk swizzle of row r: eight consecutive rows get eight different values (ldmatrix of one chunk column is
+// conflict-free), and rows r, r+1, r+2, r+3 land in four different chunk PAIRS (the scalar transposed dz loads of
+// dG, lanes = 4 rows x 8 columns, are conflict-free as well)
+__host__ __device__ constexpr int k5_swz(int r) { return ((r & 3) << 1) | ((r >> 2) & 1); }
 constexpr int kDzRows = 24;        // bases padded to three 8-wide MMA tiles
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -1088,7 +1092,7 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
     for (int k = 0; k < DZ_P; ++k) {
         const int e = lane + 32 * k, m = e >> 3, j = e & 7;
         dz_src[k] = m < M ? m * I + 4 * j : -1;
-        dz_dst[k] = (uint32_t)(m * kTS + 4 * j) * 4u;
+        dz_dst[k] = (uint32_t)(m * kTS + 4 * (j ^ k5_swz(m))) * 4u;
     }
     auto stage_dz = [&](int b, int i0, int buf) {
         const float *dzp = dz + (((size_t)b * p_out + p) * M) * I + i0;
@@ -1130,7 +1134,7 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
         const int e = lane + 32 * k, n = e >> 3, j = e & 7;
         const int q = (HAS_DA && n < l) ? idx_s[n] : -1;
         x_src[k] = q >= 0 ? q * I + 4 * j : -1;
-        x_dst[k] = x_off + (uint32_t)(n * kTS + 4 * j) * 4u;
+        x_dst[k] = x_off + (uint32_t)(n * kTS + 4 * (j ^ k5_swz(n))) * 4u;
     }
     auto stage_x = [&](int b, int i0, int buf) {
         if (!HAS_DA) return;
@@ -1142,7 +1146,7 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
         for (int e = lane + 32 * X_P; e < l * (kTC / 4); e += 32) {
             const int n = e >> 3, j = e & 7;
             const int q = idx_s[n];
-            if (q >= 0) cp_async_16(base + x_off + (uint32_t)(n * kTS + 4 * j) * 4u, xp + (size_t)q * I + 4 * j);
+            if (q >= 0) cp_async_16(base + x_off + (uint32_t)(n * kTS + 4 * (j ^ k5_swz(n))) * 4u, xp + (size_t)q * I + 4 * j);
         }
     };
     if (ct < tile_end) stage_x(b, it * kTC, 0);
@@ -1165,28 +1169,33 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
 #pragma unroll
         for (int b2 = 0; b2 < 3; ++b2) acc[a][b2][0] = acc[a][b2][1] = acc[a][b2][2] = acc[a][b2][3] = 0.f;
 
-    // ldmatrix row addresses of this lane (byte offsets inside a buffer, or -1 = the zero row). Operand A (16 x 8):
-    // matrices (rows 0-7 | 8-15) x (k 0-3 | 4-7) in the order a0..a3; operand B (8 x 8 as [n][k]): k 0-3, k 4-7.
+    // ldmatrix rows of this lane (byte offset of the row inside a buffer, or -1 = the zero row) and the row's chunk
+    // swizzle. Operand A (16 x 8): matrices (rows 0-7 | 8-15) x (k 0-3 | 4-7) in the order a0..a3; operand B (8 x 8
+    // as [n][k]): k 0-3, k 4-7. The chunk of k-block kc is 2*kc + (0|1), XORed with the row's swizzle.
     const int lr = lane & 7, lj = lane >> 3;
-    int a_off[NT16], b4_off, b2_off;
+    int a_row[NT16], a_sw[NT16], b4_row, b2_row, b4_sw, b2_sw;
 #pragma unroll
     for (int nt = 0; nt < NT16; ++nt) {
         const int n = nt * 16 + (lj & 1) * 8 + lr;
-        a_off[nt] = (n < l && idx_s[n] >= 0) ? (int)x_off + (n * kTS + (lj >> 1) * 4) * 4 : -1;
+        a_row[nt] = (n < l && idx_s[n] >= 0) ? (int)x_off + n * kTS * 4 : -1;
+        a_sw[nt] = k5_swz(n) ^ (lj >> 1);
     }
     {
         const int m4 = (lj >> 1) * 8 + lr, m2 = 16 + lr;
-        b4_off = m4 < M ? (m4 * kTS + (lj & 1) * 4) * 4 : -1;
-        b2_off = m2 < M ? (m2 * kTS + (lj & 1) * 4) * 4 : -1;
+        b4_row = m4 < M ? m4 * kTS * 4 : -1;
+        b2_row = m2 < M ? m2 * kTS * 4 : -1;
+        b4_sw = k5_swz(m4) ^ (lj & 1);
+        b2_sw = k5_swz(m2) ^ (lj & 1);
     }
     const uint32_t c_row_off = (uint32_t)(((lj & 1) * 8 + lr) * kK5S + (lj >> 1) * 4) * 4u;      // coefficient tile
     const uint32_t A_u = (uint32_t)__cvta_generic_to_shared(A_s), Al_u = (uint32_t)__cvta_generic_to_shared(Al_s);
-    // dz rows read by the scalar B-fragment loads of dG: basis ks*8 + t (+4); -1 = zero row
+    // dz words read by the scalar B-fragment loads of dG: basis ks*8 + t (+4), column c8*8 + g. In the swizzled
+    // row that is word ((c8 ^ t) * 8) + (((g >> 2) ^ (r & 1)) * 4 + (g & 3)); -1 = basis >= M (zero)
     int zrow[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
         const int m = (r >> 1) * 8 + t + (r & 1) * 4;
-        zrow[r] = m < M ? m * kTS + g : -1;
+        zrow[r] = m < M ? m * kTS + (((g >> 2) ^ (r & 1)) << 2) + (g & 3) : -1;
     }
 
     uint32_t cA[KEEP ? NT16 : 1][3][4], cAl[KEEP ? NT16 : 1][3][4];
@@ -1220,9 +1229,9 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                 uint32_t zB[3][2], zBl[3][2];
                 {
                     uint32_t r[4];
-                    ldsm_x4(r, b4_off >= 0 ? dz_u + (uint32_t)b4_off + (uint32_t)(kc * 8) * 4u : zero_u);   // bases 0-7, 8-15
+                    ldsm_x4(r, b4_row >= 0 ? dz_u + (uint32_t)b4_row + (uint32_t)(((2 * kc) ^ b4_sw) << 4) : zero_u);   // bases 0-7, 8-15
                     zB[0][0] = r[0]; zB[0][1] = r[1]; zB[1][0] = r[2]; zB[1][1] = r[3];
-                    ldsm_x2(zB[2][0], zB[2][1], b2_off >= 0 ? dz_u + (uint32_t)b2_off + (uint32_t)(kc * 8) * 4u : zero_u);
+                    ldsm_x2(zB[2][0], zB[2][1], b2_row >= 0 ? dz_u + (uint32_t)b2_row + (uint32_t)(((2 * kc) ^ b2_sw) << 4) : zero_u);
                 }
                 if (X3) {
 #pragma unroll
@@ -1232,7 +1241,7 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                 for (int nt = 0; nt < NT16; ++nt) {
                     if (NT16 > 1 && nt * 16 >= l) break;                       // warp-uniform
                     uint32_t xa[4], xal[4] = {0u, 0u, 0u, 0u};
-                    ldsm_x4(xa, a_off[nt] >= 0 ? dz_u + (uint32_t)a_off[nt] + (uint32_t)(kc * 8) * 4u : zero_u);
+                    ldsm_x4(xa, a_row[nt] >= 0 ? dz_u + (uint32_t)a_row[nt] + (uint32_t)(((2 * kc) ^ a_sw[nt]) << 4) : zero_u);
                     if (X3) {
 #pragma unroll
                         for (int r = 0; r < 4; ++r) xal[r] = tf32_lo(xa[r]);
@@ -1251,7 +1260,7 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                 uint32_t zb[3][2], zbl[3][2];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
-                    const uint32_t v = zrow[r] >= 0 ? __float_as_uint(dz_t[zrow[r] + c8 * 8]) : 0u;
+                    const uint32_t v = zrow[r] >= 0 ? __float_as_uint(dz_t[zrow[r] + ((c8 ^ t) << 3)]) : 0u;
                     zb[r >> 1][r & 1] = v;
                     if (X3) zbl[r >> 1][r & 1] = tf32_lo(v);
                 }
