@@ -1055,7 +1055,7 @@ constexpr int kNBuf = 3;           // staged tiles per warp: two in flight while
 // dA accumulates in MMA fragments over all tiles of the warp: no per-neighbour lane reduction at all. Rows that do
 // not exist (bases >= M, padding neighbours) are not staged: their ldmatrix / LDS addresses point at one zero row.
 template <int NT16, bool X3, bool HAS_DA, bool HAS_DG>
-__global__ void __launch_bounds__(128, NT16 <= 2 ? 4 : 2)
+__global__ void __launch_bounds__(128, NT16 <= 2 ? 4 : 3)
 coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
                       const float *__restrict__ dz, const float *__restrict__ x, const float *__restrict__ A,
                       float *__restrict__ dA_out, float *__restrict__ dG, int p_in, int p_out, int n_max, int I, int M,
@@ -1252,7 +1252,7 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                 }
             }
         }
-        if (HAS_DG) {
+        if (HAS_DG && KEEP) {
             float *dGp = dG + (((size_t)b * p_out + p) * n_max) * I + i0 + 2 * t;
 #pragma unroll
             for (int c8 = 0; c8 < kTC / 8; ++c8) {
@@ -1269,16 +1269,42 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
                     if (NT16 > 1 && nt * 16 >= l) break;                       // warp-uniform
                     float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) {
-                        if (KEEP) {
-                            mma_x<X3>(d, cA[nt][ks], cAl[nt][ks], zb[ks][0], zb[ks][1], zbl[ks][0], zbl[ks][1]);
-                        } else {
-                            uint32_t ca[4], cal[4] = {0u, 0u, 0u, 0u};
-                            ldsm_x4(ca, A_u + c_row_off + (uint32_t)(nt * 16 * kK5S + ks * 8) * 4u);
-                            if (X3) ldsm_x4(cal, Al_u + c_row_off + (uint32_t)(nt * 16 * kK5S + ks * 8) * 4u);
-                            mma_x<X3>(d, ca, cal, zb[ks][0], zb[ks][1], zbl[ks][0], zbl[ks][1]);
-                        }
-                    }
+                    for (int ks = 0; ks < 3; ++ks)
+                        mma_x<X3>(d, cA[nt][ks], cAl[nt][ks], zb[ks][0], zb[ks][1], zbl[ks][0], zbl[ks][1]);
+                    float *row0 = dGp + (size_t)(nt * 16 + g) * I + c8 * 8;
+                    if (st_mask & (1u << (2 * nt))) *reinterpret_cast<float2 *>(row0) = make_float2(d[0], d[1]);
+                    if (st_mask & (2u << (2 * nt))) *reinterpret_cast<float2 *>(row0 + (size_t)8 * I) = make_float2(d[2], d[3]);
+                }
+            }
+        }
+        if (HAS_DG && !KEEP) {
+            // many neighbours: the dz fragments of the whole tile stay in registers, the coefficient fragments of one
+            // 16-neighbour block are loaded once per tile
+            float *dGp = dG + (((size_t)b * p_out + p) * n_max) * I + i0 + 2 * t;
+            uint32_t zb[kTC / 8][3][2], zbl[X3 ? kTC / 8 : 1][3][2];
+#pragma unroll
+            for (int c8 = 0; c8 < kTC / 8; ++c8)
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const uint32_t v = zrow[r] >= 0 ? __float_as_uint(dz_t[zrow[r] + ((c8 ^ t) << 3)]) : 0u;
+                    zb[c8][r >> 1][r & 1] = v;
+                    if (X3) zbl[c8][r >> 1][r & 1] = tf32_lo(v);
+                }
+#pragma unroll
+            for (int nt = 0; nt < NT16; ++nt) {
+                if (nt * 16 >= l) break;                                       // warp-uniform
+                uint32_t ca[3][4], cal[3][4];
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                    ldsm_x4(ca[ks], A_u + c_row_off + (uint32_t)(nt * 16 * kK5S + ks * 8) * 4u);
+                    if (X3) ldsm_x4(cal[ks], Al_u + c_row_off + (uint32_t)(nt * 16 * kK5S + ks * 8) * 4u);
+                }
+#pragma unroll
+                for (int c8 = 0; c8 < kTC / 8; ++c8) {
+                    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks)
+                        mma_x<X3>(d, ca[ks], cal[ks], zb[c8][ks][0], zb[c8][ks][1], zbl[X3 ? c8 : 0][ks][0], zbl[X3 ? c8 : 0][ks][1]);
                     float *row0 = dGp + (size_t)(nt * 16 + g) * I + c8 * 8;
                     if (st_mask & (1u << (2 * nt))) *reinterpret_cast<float2 *>(row0) = make_float2(d[0], d[1]);
                     if (st_mask & (2u << (2 * nt))) *reinterpret_cast<float2 *>(row0 + (size_t)8 * I) = make_float2(d[2], d[3]);
