@@ -185,16 +185,29 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const float *__restrict__ 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int64_t r0 = rs; r0 < re; r0 += DR) {
+    // register prefetch of the next 16-row slab while the current one is multiplied: the slabs are tiny, the
+    // kernel is a chain of dependent global-load latencies otherwise
+    float zr[4], dr[4];
+    auto fetch = [&](int64_t r0) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = tid + 256 * u;
             const int rr = e >> 6, cc = e & 63;
             const int64_t r = r0 + rr;
-            Zs[rr][cc] = (r < re && k0 + cc < K) ? __ldg(z + (size_t)r * K + k0 + cc) : 0.f;
-            Ds[rr][cc] = (r < re && o0 + cc < O) ? __ldg(ds + (size_t)r * O + o0 + cc) : 0.f;
+            zr[u] = (r < re && k0 + cc < K) ? __ldg(z + (size_t)r * K + k0 + cc) : 0.f;
+            dr[u] = (r < re && o0 + cc < O) ? __ldg(ds + (size_t)r * O + o0 + cc) : 0.f;
+        }
+    };
+    fetch(rs);
+    for (int64_t r0 = rs; r0 < re; r0 += DR) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + 256 * u;
+            Zs[e >> 6][e & 63] = zr[u];
+            Ds[e >> 6][e & 63] = dr[u];
         }
         __syncthreads();
+        if (r0 + DR < re) fetch(r0 + DR);
 #pragma unroll
         for (int rr = 0; rr < DR; ++rr) {
             const float4 a = *reinterpret_cast<const float4 *>(&Zs[rr][ty * 4]);
@@ -222,16 +235,29 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const float *__restrict__ 
 
 // dW[m][o][i] = sum_s part[s][k = m*I+i][o], fixed order. Threads walk the partial layout (coalesced reads,
 // n_split of them per element); the single write per element goes to dW's native layout.
+// 256 threads = 32 elements x 8 groups of splits: every group sums its contiguous share of the splits in order, the
+// eight group sums are added in order through shared memory (the chain of dependent loads is n_split / 8 long).
 __global__ void reduce_dw_kernel(const float *__restrict__ part, float *__restrict__ dW, int K, int O, int I,
                                  int n_split) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into part[s]: k * O + o
-    if (e >= (size_t)K * O) return;
-    const int o = (int)(e % O);
-    const int k = (int)(e / O);
-    const int m = k / I, i = k - m * I;
+    __shared__ float red[8][32];
+    const int le = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const size_t e = (size_t)blockIdx.x * 32 + le;                    // index into part[s]: k * O + o
+    const bool in = e < (size_t)K * O;
+    const int per = (n_split + 7) / 8, j0 = grp * per, j1 = min(n_split, j0 + per);
     float s = 0.f;
-    for (int j = 0; j < n_split; ++j) s += part[(size_t)j * K * O + e];
-    dW[((size_t)m * O + o) * I + i] = s;
+    if (in)
+        for (int j = j0; j < j1; ++j) s += part[(size_t)j * K * O + e];
+    red[grp][le] = s;
+    __syncthreads();
+    if (grp == 0 && in) {
+        float tot = red[0][le];
+#pragma unroll
+        for (int g2 = 1; g2 < 8; ++g2) tot += red[g2][le];
+        const int o = (int)(e % O);
+        const int k = (int)(e / O);
+        const int m = k / I, i = k - m * I;
+        dW[((size_t)m * O + o) * I + i] = tot;
+    }
 }
 
 // ds / dbias / dres in one pass; one thread per (p, o), loop over the batch. The batch loop is blocked by 8
@@ -350,7 +376,7 @@ int simt_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t R, int
 }
 
 int reduce_dw_partials(const float *part, float *dW, int K, int O, int I, int n_split, cudaStream_t st) {
-    reduce_dw_kernel<<<(unsigned)ceil_div((int64_t)K * O, 256), 256, 0, st>>>(part, dW, K, O, I, n_split);
+    reduce_dw_kernel<<<(unsigned)ceil_div((int64_t)K * O, 32), 256, 0, st>>>(part, dW, K, O, I, n_split);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
@@ -367,7 +393,7 @@ int simt_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int
     dim3 grid((unsigned)ceil_div(K, DK), (unsigned)ceil_div(O, DO), (unsigned)p.n_split);
     gemm_tn_kernel<<<grid, 256, 0, st>>>(z, ds, ws, R, K, O, p.rows_per_split);
     VCM_LAUNCH_CHECK();
-    reduce_dw_kernel<<<(unsigned)ceil_div((int64_t)K * O, 256), 256, 0, st>>>(ws, dW, K, O, I, p.n_split);
+    reduce_dw_kernel<<<(unsigned)ceil_div((int64_t)K * O, 32), 256, 0, st>>>(ws, dW, K, O, I, p.n_split);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
