@@ -48,3 +48,9 @@ for e in k:
     a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += e["dur"]
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
     print("%8.1f us x%-3d %s" % (t, c, n))
+
+tor = {n: v for n, v in agg.items() if not n.startswith("vcm::")}
+print("torch glue: %d kernels, %.1f us; ours: %d kernels, %.1f us" % (sum(v[0] for v in tor.values()), sum(v[1] for v in tor.values()),
+      sum(v[0] for n, v in agg.items() if n.startswith("vcm::")), sum(v[1] for n, v in agg.items() if n.startswith("vcm::"))))
+for n, (c, t) in sorted(tor.items(), key=lambda kv: -kv[1][1]):
+    print("   glue %8.1f us x%-3d %s" % (t, c, n[:150]))
