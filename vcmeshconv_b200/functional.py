@@ -263,12 +263,40 @@ def _basis_backward(z, W, y, dout, cfg, need, dW_target, db_target):
         direct_dW = dW_target is not None
         dW = dW_target if direct_dW else torch.empty_like(W)
         n_ws = L.vcm_basis_bwd_dw_workspace(R, M, I, O, precision)
-        ws = torch.empty(max(n_ws, 1), device=dev, dtype=torch.float32)
-        _lib.call("vcm_basis_bwd_dw", _ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision, st,
-                  nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
+        if direct_dW and _side_stream is not None:
+            # dW depends on (ds, z) only and nothing downstream of this layer reads it: it runs as a parallel branch
+            # (second stream; a parallel branch of the captured graph) next to the dz -> K5 -> K6 chain
+            cur = torch.cuda.current_stream()
+            _side_stream.wait_stream(cur)
+            with torch.cuda.stream(_side_stream):
+                ws = torch.empty(max(n_ws, 1), device=dev, dtype=torch.float32)
+                _lib.call("vcm_basis_bwd_dw", _ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision,
+                          _lib.stream_ptr(), nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
+            _side_keep.append((ds, z, ws))            # their memory must not be recycled before the join
+        else:
+            ws = torch.empty(max(n_ws, 1), device=dev, dtype=torch.float32)
+            _lib.call("vcm_basis_bwd_dw", _ptr(ds), _ptr(z), _ptr(dW), _ptr(ws), R, M, I, O, precision, st,
+                      nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
         if direct_dW:
             dW = None
     return dz, dW, dbias, dres
+
+
+# Optional second stream for the dW GEMMs of a backward pass (set by the trainer, which also joins it).
+_side_stream = None
+_side_keep = []
+
+
+def set_side_stream(stream):
+    global _side_stream
+    _side_stream = stream
+
+
+def join_side_stream():
+    """The current stream waits for the branch; buffers parked for it are released."""
+    if _side_stream is not None:
+        torch.cuda.current_stream().wait_stream(_side_stream)
+    _side_keep.clear()
 
 
 class _FusedConv(torch.autograd.Function):

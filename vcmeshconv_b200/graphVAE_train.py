@@ -177,6 +177,9 @@ class DataParallelTrainer:
         # optimizer scalars live on the device so a captured step can be replayed: {step, lr, 1-b1^t, sqrt(1-b2^t)}
         self.opt_state = torch.tensor([0.0, lr, 0.0, 0.0], device=self.flat.flat_p.device, dtype=torch.float32)
         self._graph = None
+        # dW GEMMs on a second stream (parallel graph branch); VCM_DW_STREAM=0 turns it off
+        self.dw_stream = (torch.cuda.Stream(self.flat.flat_p.device)
+                          if self.flat.flat_p.is_cuda and os.environ.get("VCM_DW_STREAM", "1") == "1" else None)
         self.overlap = overlap and self.world > 1
         self._pending = []
         self._handles = []
@@ -239,7 +242,13 @@ class DataParallelTrainer:
         self.flat.zero_grad()
         F_.begin_step(self.flat.params)
         loss, l1, lap, kl, lnor, _ = self.model.losses(pc, nor, eps)
-        loss.backward()
+        if self.dw_stream is not None and not self.overlap:
+            F_.set_side_stream(self.dw_stream)
+        try:
+            loss.backward()
+        finally:
+            F_.join_side_stream()
+            F_.set_side_stream(None)
         return loss.detach(), (l1.detach(), lap.detach(), kl.detach(), lnor.detach())
 
     @property
