@@ -6,6 +6,7 @@ import torch
 
 from helpers import rel_err
 from vcmeshconv_b200 import _lib
+from vcmeshconv_b200 import functional as F_
 from vcmeshconv_b200 import graphVAE_train as T
 
 pytestmark = pytest.mark.gpu
@@ -106,6 +107,49 @@ def test_fit_loop_follows_reference_schedule(tmp_path):
     import os
     assert sorted(os.listdir(param.write_weight_folder)) == ["model_00000%02d_best.weight" % i for i in (10, 12, 14)]
     assert abs(tr.lr - 1e-3 * 0.99 ** 2) < 1e-12 and abs(tr.opt_state[1].item() - tr.lr) < 1e-9
+
+
+def _c2_like(seed, streams):
+    """Full 6+6-layer autoencoder on a 3000-vertex sphere, batch 16 (kernels long enough to really overlap)."""
+    from vcmeshconv_b200 import synthetic
+    model, pts, faces, tabs, nums = T.build_synthetic_autoencoder(3000, seed=0)
+    model = model.cuda()
+    tr = T.DataParallelTrainer(model, lr=1e-3)
+    if not streams:
+        tr.dw_stream = tr.res_stream = None
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pc = torch.from_numpy(pts)[None].repeat(16, 1, 1).cuda() * 0.9 + torch.randn(16, len(pts), 3, device="cuda", generator=g) * 0.02
+    nor = torch.from_numpy(synthetic.face_normals(pc.cpu().numpy(), faces)).float().cuda()
+    return tr, pc, nor
+
+
+def test_parallel_branches_do_not_change_results():
+    """The dW GEMMs and the residual branch of every layer run on their own streams (parallel branches of the
+    captured graph). Eager: gradients and three trained steps equal the single-stream run (the only freedom is
+    the order in which autograd adds the two or three gradients of a shared input). Captured: ten replays from
+    the same RNG state give the same parameters as ten single-stream replays."""
+    prev = F_.set_precision("tf32")
+    try:
+        tr1, pc, nor = _c2_like(1, streams=False)
+        tr2, _, _ = _c2_like(1, streams=True)
+        assert tr2.dw_stream is not None and tr2.res_stream is not None
+        eps = torch.randn(16, tr1.model.nrpt_latent, 64, device="cuda")
+        for it in range(3):
+            l1, _ = tr1.step(pc, nor, eps=eps)
+            l2, _ = tr2.step(pc, nor, eps=eps)
+            torch.cuda.synchronize()
+            assert rel_err(tr2.flat.flat_g.cpu().numpy(), tr1.flat.flat_g.cpu().numpy()) < 1e-5
+            assert abs(l1.item() - l2.item()) <= 1e-5 * abs(l1.item())
+        assert rel_err(tr2.flat.flat_p.cpu().numpy(), tr1.flat.flat_p.cpu().numpy()) < 1e-5
+        for tr in (tr1, tr2):
+            torch.manual_seed(123)
+            tr.capture(pc, nor, warmup=1)
+            for _ in range(10):
+                tr.step(pc, nor)
+        torch.cuda.synchronize()
+        assert rel_err(tr2.flat.flat_p.cpu().numpy(), tr1.flat.flat_p.cpu().numpy()) < 1e-4
+    finally:
+        F_.set_precision(prev)
 
 
 def test_graph_captured_step_matches_eager():

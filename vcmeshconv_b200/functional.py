@@ -292,6 +292,20 @@ def set_side_stream(stream):
     _side_stream = stream
 
 
+# Optional stream for the residual branch of every layer (forward; autograd replays a node's backward on the
+# stream of its forward, so the branch's backward overlaps the main chain as well). Set by the trainer.
+_residual_stream = None
+
+
+def set_residual_stream(stream):
+    global _residual_stream
+    _residual_stream = stream
+
+
+def residual_stream():
+    return _residual_stream
+
+
 def join_side_stream():
     """The current stream waits for the branch; buffers parked for it are released."""
     if _side_stream is not None:

@@ -116,8 +116,9 @@ class LASMConvssw(nn.Module):
             res, sy, sr = self._residual(in_pc, t)
             return F_.fused_conv(in_pc, raw_w_weights, self.weights, self.bias, res, t, M, I, O, not is_final_layer,
                                  sy, sr)
+        branch = self._residual_fork(in_pc, t)
         z = F_.gather_contract(in_pc, raw_w_weights, t)
-        return self.forward_from_z(z, in_pc, is_final_layer)
+        return self.forward_from_z(z, in_pc, is_final_layer, branch)
 
     def _residual(self, in_pc, t):
         """graphVAESSW.py:144-159 -> (res or None, scale_y, scale_res)."""
@@ -135,9 +136,28 @@ class LASMConvssw(nn.Module):
             return project(F_.gather_contract(in_pc, pn, t)), sy, sr
         return F_.gather_contract(project(in_pc), pn, t), sy, sr
 
+    def _residual_fork(self, in_pc, t):
+        """Runs the residual branch on the trainer's second stream when there is one: it only meets the main chain
+        again in the epilogue (join in `_residual_join`). Returns ((res, sy, sr), stream or None)."""
+        side = F_.residual_stream()
+        if side is None or self.residual_rate == 0 or not in_pc.is_cuda:
+            return self._residual(in_pc, t), None
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            r = self._residual(in_pc, t)
+        return r, side
+
+    @staticmethod
+    def _residual_join(branch):
+        r, side = branch
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        return r
+
     def _forward_project_first(self, in_pc, raw_w_weights, is_final_layer):
         B = in_pc.shape[0]
         M, I, O = self.weight_num, self.in_channel, self.out_channel
+        branch = self._residual_fork(in_pc, self.tables(in_pc.device))
         # u[b,q,m,:] = W_m x[b,q,:]: one GEMM with the bases stacked along the output axis ([1][M*O][I] view)
         u = F_.basis_gemm(in_pc, self.weights.view(1, M * O * I), None, None, 1, I, M * O, False)
         t = self.tables(in_pc.device)
@@ -147,16 +167,16 @@ class LASMConvssw(nn.Module):
             tx = self.tables_expanded(in_pc.device)
             s = F_.gather_contract(u.view(B, self.in_point_num * M, O),
                                    raw_w_weights.reshape(self.out_point_num, self.max_neighbor_num * M, 1), tx)
-        res, sy, sr = self._residual(in_pc, self.tables(in_pc.device))
+        res, sy, sr = self._residual_join(branch)
         return F_.bias_act(s, self.bias, res, not is_final_layer, sy, sr)
 
-    def forward_from_z(self, z, in_pc, is_final_layer=False):
+    def forward_from_z(self, z, in_pc, is_final_layer=False, branch=None):
         """Stage 2 on an already contracted z (lets two layers that share input,
         table and coefficients — the encoder's mu / std heads — share stage 1)."""
         t = self.tables(in_pc.device)
         M, I, O = self.weight_num, self.in_channel, self.out_channel
         act = not is_final_layer
-        res, sy, sr = self._residual(in_pc, t)
+        res, sy, sr = self._residual_join(branch if branch is not None else self._residual_fork(in_pc, t))
         return F_.basis_gemm(z, self.weights, self.bias, res, M, I, O, act, sy, sr)
 
     # the reference keeps its original, memory-hungry formulation as `forward2`

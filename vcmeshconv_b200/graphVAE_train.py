@@ -180,6 +180,9 @@ class DataParallelTrainer:
         # dW GEMMs on a second stream (parallel graph branch); VCM_DW_STREAM=0 turns it off
         self.dw_stream = (torch.cuda.Stream(self.flat.flat_p.device)
                           if self.flat.flat_p.is_cuda and os.environ.get("VCM_DW_STREAM", "1") == "1" else None)
+        # residual branch of every layer on its own stream (forward, and through autograd its backward)
+        self.res_stream = (torch.cuda.Stream(self.flat.flat_p.device)
+                           if self.flat.flat_p.is_cuda and os.environ.get("VCM_RES_STREAM", "1") == "1" else None)
         self.overlap = overlap and self.world > 1
         self._pending = []
         self._handles = []
@@ -241,7 +244,12 @@ class DataParallelTrainer:
     def forward_backward(self, pc, nor, eps=None):
         self.flat.zero_grad()
         F_.begin_step(self.flat.params)
-        loss, l1, lap, kl, lnor, _ = self.model.losses(pc, nor, eps)
+        if self.res_stream is not None and not self.overlap:
+            F_.set_residual_stream(self.res_stream)
+        try:
+            loss, l1, lap, kl, lnor, _ = self.model.losses(pc, nor, eps)
+        finally:
+            F_.set_residual_stream(None)
         if self.dw_stream is not None and not self.overlap:
             F_.set_side_stream(self.dw_stream)
         try:
