@@ -243,19 +243,25 @@ def run_ours(args):
         pc, nor = resident[i % n_rot]
         trainer.step(pc, nor)
 
-    dev_pc = torch.empty_like(resident[0][0])
-    dev_nor = torch.empty_like(resident[0][1])
-    loss_host = torch.zeros(1).pin_memory()
-    h2d = dev_pc.numel() * 4 + dev_nor.numel() * 4
+    # End to end through the trainer's host-fed API: every step copies ITS batch from pinned host memory (staged on a
+    # copy stream while the previous step runs) and its loss goes back to pinned host memory; the host reads each
+    # loss value one step later, so it never runs more than two steps ahead of the device.
+    loss_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
+    loss_ev = [None, None]
+    loss_seen = []
+    h2d = resident[0][0].numel() * 4 + resident[0][1].numel() * 4
 
     def step_e2e(i):
-        hp, hn = pin[i % n_rot]
-        tp = trainer.static_pc if trainer._graph is not None else dev_pc
-        tn = trainer.static_nor if trainer._graph is not None else dev_nor
-        tp.copy_(hp, non_blocking=True)                            # pinned host -> device, inside the timed region
-        tn.copy_(hn, non_blocking=True)
-        loss, _ = trainer.step(tp, tn)
-        loss_host.copy_(loss.reshape(1), non_blocking=False)       # device -> host read of the step's result
+        loss, _ = trainer.step_prefetched()                        # consumes the batch staged for step i
+        hp, hn = pin[(i + 1) % n_rot]
+        trainer.prefetch(hp, hn)                                   # pinned host -> device for step i + 1
+        s2 = i & 1
+        if loss_ev[s2] is not None:
+            loss_ev[s2].synchronize()
+            loss_seen.append(float(loss_host[s2][0]))              # the host consumes the loss of step i - 2
+        loss_host[s2].copy_(loss.reshape(1), non_blocking=True)    # device -> host read of the step's result
+        loss_ev[s2] = torch.cuda.Event()
+        loss_ev[s2].record()
 
     if not args.no_graph:
         trainer.capture(resident[0][0], resident[0][1], warmup=2)
@@ -264,6 +270,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches, t0, t1 = timed(step_resident, args.steps)
     clocks = sampler.stop(t0, t1) if sampler else None
+    trainer.prefetch(*pin[0])
     for i in range(2):
         step_e2e(i)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)

@@ -152,6 +152,32 @@ def test_parallel_branches_do_not_change_results():
         F_.set_precision(prev)
 
 
+def test_host_fed_steps_match_resident_steps():
+    """prefetch() / step_prefetched(): the batch staged from pinned host memory on the copy stream gives the same
+    training trajectory as steps on resident tensors."""
+    trs = []
+    for _ in range(2):
+        model, pc, nor = _small_model(4)
+        tr = T.DataParallelTrainer(model, lr=1e-3)
+        torch.manual_seed(77)
+        tr.capture(pc, nor, warmup=1)
+        trs.append((tr, pc, nor))
+    (tr1, pc, nor), (tr2, _, _) = trs
+    hp, hn = (pc * 1.01).cpu().pin_memory(), nor.cpu().pin_memory()
+    dp, dn = hp.cuda(), hn.cuda()
+    torch.manual_seed(5)                      # the replays draw eps from the global generator: same state for both runs
+    for _ in range(6):
+        l1, _ = tr1.step(dp, dn)
+    torch.manual_seed(5)
+    tr2.prefetch(hp, hn)
+    for _ in range(6):
+        l2, _ = tr2.step_prefetched()
+        tr2.prefetch(hp, hn)
+    torch.cuda.synchronize()
+    assert abs(l1.item() - l2.item()) <= 1e-5 * abs(l1.item())
+    assert rel_err(tr2.flat.flat_p.cpu().numpy(), tr1.flat.flat_p.cpu().numpy()) < 1e-5
+
+
 def test_graph_captured_step_matches_eager():
     """The CUDA-graph replay of the step produces the same parameters as eager steps
     (fixed eps is not used: the encoder's N(0,1) draw comes from the graph-safe generator,

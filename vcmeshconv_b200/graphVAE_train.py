@@ -177,6 +177,7 @@ class DataParallelTrainer:
         # optimizer scalars live on the device so a captured step can be replayed: {step, lr, 1-b1^t, sqrt(1-b2^t)}
         self.opt_state = torch.tensor([0.0, lr, 0.0, 0.0], device=self.flat.flat_p.device, dtype=torch.float32)
         self._graph = None
+        self._copy_stream = None
         # dW GEMMs on a second stream (parallel graph branch); VCM_DW_STREAM=0 turns it off
         self.dw_stream = (torch.cuda.Stream(self.flat.flat_p.device)
                           if self.flat.flat_p.is_cuda and os.environ.get("VCM_DW_STREAM", "1") == "1" else None)
@@ -283,6 +284,40 @@ class DataParallelTrainer:
         self._finish_reduction()
         self.optimizer_step()
         return loss, parts
+
+    # -- host-fed steps: the next batch is staged while the current step runs ---------------
+    def prefetch(self, host_pc, host_nor):
+        """Starts the host -> device copy of the NEXT batch (pinned host tensors) on a copy stream; the batch is
+        consumed by the following `step_prefetched()`. Two staging slots alternate, so the copy overlaps the step
+        that is running."""
+        dev = self.flat.flat_p.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage = [(torch.empty(host_pc.shape, device=dev), torch.empty(host_nor.shape, device=dev))
+                           for _ in range(2)]
+            self._stage_free = [None, None]
+            self._stage_i = 0
+        slot = self._stage_i
+        self._stage_i ^= 1
+        buf = self._stage[slot]
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_free[slot] is not None:
+                self._copy_stream.wait_event(self._stage_free[slot])     # the step that read this slot is done
+            buf[0].copy_(host_pc, non_blocking=True)
+            buf[1].copy_(host_nor, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        self._staged = (slot, ready)
+
+    def step_prefetched(self):
+        slot, ready = self._staged
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready)
+        out = self.step(*self._stage[slot])
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._stage_free[slot] = done
+        return out
 
     # -- CUDA-graph capture of the step -----------------------------------------------
     def capture(self, pc, nor, warmup=3):
