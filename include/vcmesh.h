@@ -233,6 +233,45 @@ VCM_API int vcm_adam_step(float *p, const float *g, float *m, float *v, size_t n
 VCM_API int vcm_adam_step_graph(float *p, const float *g, float *m, float *v, size_t n, float *state, float beta1,
                                 float beta2, float eps, float grad_scale, void *stream);
 
+/* ------------------------------------------------------------- loss head --
+ * The autoencoder's loss glue (GraphAutoEncoder/graphVAE_train.py:199-225) as four
+ * launches instead of ~110 few-microsecond ATen kernels between the decoder's last
+ * kernel and the first backward kernel. Deterministic (fixed-order
+ * partial sums, reverse-CSR gathers, no atomics).
+ *
+ * Reparameterisation + KL term (graphVAE_train.py:199-206; the two encoder heads are
+ * scaled by scale_mu / scale_logstd as MCEnc.forward does, graphVAESSW.py:286-288):
+ *   mu = raw_mu*scale_mu, ls = raw_logstd*scale_logstd, z = mu + exp(ls)*eps,
+ *   kl[0] = mean(-0.5 - ls + 0.5 mu^2 + 0.5 exp(2 ls)).  All arrays have n elements.
+ * workspace: fp32, vcm_reparam_kl_workspace(n) elements (NULL when that is 0).
+ * Backward: dz [n] and dkl [1] (device scalars; either may be NULL = zero). */
+VCM_API size_t vcm_reparam_kl_workspace(size_t n);
+VCM_API int vcm_reparam_kl_fwd(const float *raw_mu, const float *raw_logstd, const float *eps, float *z, float *kl,
+                               float *workspace, size_t n, float scale_mu, float scale_logstd, void *stream);
+VCM_API int vcm_reparam_kl_bwd(const float *raw_mu, const float *raw_logstd, const float *eps, const float *dz,
+                               const float *dkl, float *d_raw_mu, float *d_raw_logstd, size_t n, float scale_mu,
+                               float scale_logstd, void *stream);
+
+/* Geometric losses on out / gt [B,P,3] and face normals nor [B,F,3]:
+ *   l1  = mean |gt - out|                                  graphVAESSW.py:416-421
+ *   lap = mean_{b,p} |L(gt - out)[b,p]|^2, L(e)[p] = sum_n lap_coef[p,n] e[idx[p,n]]
+ *         over the layer-0 table `lap` (coef = cnt_p for slot 0, -1 elsewhere)
+ *                                                          graphVAESSW.py:507-542
+ *   nor = mean_{b,f} ((sum_k (out - gt)[face[f,k]]) / 3 . nor[b,f])^2 over the
+ *         one-row-per-face table `faces` ([F, 1+2*3])      graphVAE_train.py:212-217
+ *   total[0] = w_pose*l1 + w_lap*lap + w_nor*nor  (:225 without KL), parts[3] = {l1, lap, nor}
+ * The forward also stores lapv [B,P,3] = L(gt - out) and s [B,F] (the per-face dot
+ * products) for the backward, which writes d_out = g_total[0] * d(total)/d(out).
+ * workspace: fp32, vcm_loss_head_workspace() elements. */
+VCM_API size_t vcm_loss_head_workspace(const vcm_tables *lap, const vcm_tables *faces, int B);
+VCM_API int vcm_loss_head_fwd(const vcm_tables *lap, const vcm_tables *faces, const float *lap_coef, const float *out,
+                              const float *gt, const float *nor, float *lapv, float *s, float *total, float *parts,
+                              float *workspace, int B, float w_pose, float w_lap, float w_nor, void *stream);
+VCM_API int vcm_loss_head_bwd(const vcm_tables *lap, const vcm_tables *faces, const float *lap_coef, const float *out,
+                              const float *gt, const float *nor, const float *lapv, const float *s,
+                              const float *g_total, float *d_out, int B, float w_pose, float w_lap, float w_nor,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

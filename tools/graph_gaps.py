@@ -40,6 +40,22 @@ for r in range(NREP):
           % (r, span, busy, sum(pos), len(pos), sorted(pos)[len(pos) // 2] if pos else 0, max(pos) if pos else 0,
              sum(1 for g in gaps if g <= 0)))
 k = ev[(NREP - 1) * per:]
+if len(sys.argv) > 1:                      # timeline of the last replay: start (us from the first kernel), duration, stream, name
+    with open(sys.argv[1], "w") as f:
+        t0 = k[0]["ts"]
+        for e in k:
+            a = e.get("args", {})
+            f.write("%.2f\t%.2f\t%s\t%s\t%s\n" % (e["ts"] - t0, e["dur"], a.get("stream", ""), a.get("grid", ""),
+                                                  e["name"].replace("void ", "")[:160]))
+    iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in k)
+    busy_u, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
+    for s_, e_ in iv[1:]:
+        if s_ > cur_e:
+            busy_u += cur_e - cur_s; cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    busy_u += cur_e - cur_s
+    print("last replay: union of kernel intervals %.1f us, no kernel running for %.1f us" % (busy_u, iv[-1][1] if False else (max(e for _, e in iv) - iv[0][0] - busy_u)))
 small = sum(1 for e in k if e["dur"] < 5); print("kernels < 5 us: %d (sum %.1f us)" % (small, sum(e["dur"] for e in k if e["dur"] < 5)))
 agg = {}
 for e in k:

@@ -59,6 +59,12 @@ SIGNATURES = {
     "vcm_basis_bwd_dw": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
     "vcm_adam_step": (_i, [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _i, _f, _p]),
     "vcm_adam_step_graph": (_i, [_p, _p, _p, _p, _sz, _p, _f, _f, _f, _f, _p]),
+    "vcm_reparam_kl_workspace": (_sz, [_sz]),
+    "vcm_reparam_kl_fwd": (_i, [_p, _p, _p, _p, _p, _p, _sz, _f, _f, _p]),
+    "vcm_reparam_kl_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _f, _f, _p]),
+    "vcm_loss_head_workspace": (_sz, [_p, _p, _i]),
+    "vcm_loss_head_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _p]),
+    "vcm_loss_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _p]),
 }
 
 

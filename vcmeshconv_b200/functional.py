@@ -6,6 +6,8 @@ autograd tape. Every arithmetic step of the layer is one of our kernels:
   gather_contract   K1 fwd / K5 + K6 bwd       graphVAESSW.py:111-123
   basis_gemm        K2 fwd / act_bwd+K3+K4 bwd graphVAESSW.py:125-138, :161
   edge_weights      residual |p| normalisation graphVAESSW.py:155-157
+  reparam_kl        z = mu + std*eps, KL term    graphVAE_train.py:199-206
+  loss_head         l1 + laplace + normal losses graphVAE_train.py:212-225
   vcconv            the whole layer            graphVAESSW.py:97-163
 
 Tensors must be CUDA fp32; CPU tensors raise (no fallback).
@@ -440,6 +442,100 @@ class _EdgeWeights(torch.autograd.Function):
         _lib.call("vcm_edge_weights_bwd", ctx.tables.handle, _ptr(p_nb), _ptr(dpn), _ptr(dp), _lib.stream_ptr(),
                   nbytes=16 * p_nb.numel(), flops=6 * p_nb.numel())
         return (None if direct else dp), None
+
+
+class _ReparamKL(torch.autograd.Function):
+    """(z, kl) of graphVAE_train.py:199-206 from the two UNSCALED encoder heads (MCEnc scales them by 0.1 / 0.01,
+    graphVAESSW.py:286-288): one launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, raw_mu, raw_logstd, eps, scale_mu, scale_logstd):
+        raw_mu, raw_logstd, eps = _req(raw_mu, "mu head"), _req(raw_logstd, "log-std head"), _req(eps, "eps")
+        if raw_mu.shape != raw_logstd.shape or eps.shape != raw_mu.shape:
+            raise RuntimeError("mu, log-std and eps must have one shape, got %s %s %s" %
+                               (tuple(raw_mu.shape), tuple(raw_logstd.shape), tuple(eps.shape)))
+        n = raw_mu.numel()
+        z = torch.empty_like(raw_mu)
+        kl = torch.empty((), device=raw_mu.device, dtype=torch.float32)
+        n_ws = _lib.lib().vcm_reparam_kl_workspace(n)
+        ws = torch.empty(n_ws, device=raw_mu.device, dtype=torch.float32) if n_ws else None
+        _lib.call("vcm_reparam_kl_fwd", _ptr(raw_mu), _ptr(raw_logstd), _ptr(eps), _ptr(z), _ptr(kl), _ptr(ws), n,
+                  scale_mu, scale_logstd, _lib.stream_ptr(), nbytes=16 * n, flops=12 * n, tag="n%d" % n)
+        ctx.save_for_backward(raw_mu, raw_logstd, eps)
+        ctx.scales = (scale_mu, scale_logstd)
+        return z, kl
+
+    @staticmethod
+    def backward(ctx, dz, dkl):
+        raw_mu, raw_logstd, eps = ctx.saved_tensors
+        n = raw_mu.numel()
+        dz = _req(dz, "dz") if dz is not None else None
+        dkl = _req(dkl, "dkl") if dkl is not None else None
+        d_mu, d_ls = torch.empty_like(raw_mu), torch.empty_like(raw_logstd)
+        _lib.call("vcm_reparam_kl_bwd", _ptr(raw_mu), _ptr(raw_logstd), _ptr(eps), _ptr(dz), _ptr(dkl), _ptr(d_mu),
+                  _ptr(d_ls), n, ctx.scales[0], ctx.scales[1], _lib.stream_ptr(), nbytes=24 * n, flops=12 * n,
+                  tag="n%d" % n)
+        return d_mu, d_ls, None, None, None
+
+
+class _LossHead(torch.autograd.Function):
+    """(total = w_pose*l1 + w_lap*laplace + w_nor*normal, parts = [l1, laplace, normal]) of
+    graphVAE_train.py:212-225 (KL excluded) in two launches; the backward is one launch. Only total is
+    differentiable."""
+
+    @staticmethod
+    def forward(ctx, out_pc, gt_pc, nor, lap_coef, lap_tables, face_tables, w_pose, w_lap, w_nor):
+        out_pc, gt_pc, nor = _req(out_pc, "out_pc"), _req(gt_pc, "gt_pc"), _req(nor, "face normals")
+        lap_coef = _req(lap_coef, "laplacian coefficients")
+        B, P, C = out_pc.shape
+        F = face_tables.p_out
+        if C != 3 or tuple(gt_pc.shape) != (B, P, 3) or tuple(nor.shape) != (B, F, 3):
+            raise RuntimeError("loss head needs out/gt [B,%d,3] and normals [B,%d,3], got %s %s %s" %
+                               (P, F, tuple(out_pc.shape), tuple(gt_pc.shape), tuple(nor.shape)))
+        if lap_tables.p_out != P or lap_coef.numel() != P * lap_tables.n_max:
+            raise RuntimeError("laplacian table / coefficients do not match %d vertices" % P)
+        dev = out_pc.device
+        lapv = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
+        s = torch.empty(B, F, device=dev, dtype=torch.float32)
+        total = torch.empty((), device=dev, dtype=torch.float32)
+        parts = torch.empty(3, device=dev, dtype=torch.float32)
+        ws = torch.empty(_lib.lib().vcm_loss_head_workspace(lap_tables.handle, face_tables.handle, B), device=dev,
+                         dtype=torch.float32)
+        nb = 4 * (2 * B * P * 3 * 2 + lap_tables.nnz * 2 + B * F * 4 + B * P * 3 + B * F)
+        _lib.call("vcm_loss_head_fwd", lap_tables.handle, face_tables.handle, _ptr(lap_coef), _ptr(out_pc), _ptr(gt_pc),
+                  _ptr(nor), _ptr(lapv), _ptr(s), _ptr(total), _ptr(parts), _ptr(ws), B, w_pose, w_lap, w_nor, _lib.stream_ptr(),
+                  nbytes=nb, flops=B * (6 * lap_tables.nnz + 20 * F + 12 * P), tag="P%d F%d" % (P, F))
+        ctx.save_for_backward(out_pc, gt_pc, nor, lap_coef, lapv, s)
+        ctx.cfg = (lap_tables, face_tables, w_pose, w_lap, w_nor)
+        ctx.mark_non_differentiable(parts)
+        return total, parts
+
+    @staticmethod
+    def backward(ctx, g_total, _g_parts):
+        out_pc, gt_pc, nor, lap_coef, lapv, s = ctx.saved_tensors
+        lap_tables, face_tables, w_pose, w_lap, w_nor = ctx.cfg
+        B, P, _ = out_pc.shape
+        g_total = _req(g_total, "d loss")
+        d_out = torch.empty_like(out_pc)
+        nb = 4 * (B * P * 3 * 4 + lap_tables.nnz * 2 + B * face_tables.nnz * 4)
+        _lib.call("vcm_loss_head_bwd", lap_tables.handle, face_tables.handle, _ptr(lap_coef), _ptr(out_pc), _ptr(gt_pc),
+                  _ptr(nor), _ptr(lapv), _ptr(s), _ptr(g_total), _ptr(d_out), B, w_pose, w_lap, w_nor,
+                  _lib.stream_ptr(), nbytes=nb, flops=B * (6 * lap_tables.nnz + 6 * face_tables.nnz + 12 * P),
+                  tag="P%d F%d" % (P, face_tables.p_out))
+        d_gt = -d_out if ctx.needs_input_grad[1] else None
+        return d_out, d_gt, None, None, None, None, None, None, None
+
+
+def reparam_kl(raw_mu, raw_logstd, eps, scale_mu=1.0, scale_logstd=1.0):
+    """z = mu + exp(logstd)*eps and the KL term mean(-0.5 - logstd + 0.5 mu^2 + 0.5 exp(2 logstd)) with
+    mu = raw_mu*scale_mu, logstd = raw_logstd*scale_logstd. Returns (z, kl scalar)."""
+    return _ReparamKL.apply(raw_mu, raw_logstd, eps, float(scale_mu), float(scale_logstd))
+
+
+def loss_head(out_pc, gt_pc, nor, lap_coef, lap_tables, face_tables, w_pose, w_lap, w_nor):
+    """(w_pose*l1 + w_lap*laplace + w_nor*normal, [l1, laplace, normal]) on out/gt [B,P,3], face normals [B,F,3]."""
+    return _LossHead.apply(out_pc, gt_pc, nor, lap_coef, lap_tables, face_tables, float(w_pose), float(w_lap),
+                           float(w_nor))
 
 
 def gather_contract(x, coeffs, tables):

@@ -220,7 +220,10 @@ class MCEnc(nn.Module):
                                        b_max_pool=self.b_max_pool)
         return out_pc
 
-    def forward(self, in_pc, vcoeffs):
+    MU_SCALE, LOGSTD_SCALE = 0.1, 0.01           # graphVAESSW.py:286-288
+
+    def forward_raw(self, in_pc, vcoeffs):
+        """The two heads before their scaling (the fused reparameterisation kernel applies MU_SCALE / LOGSTD_SCALE)."""
         last = self.layer_num - 1
         h = self.forward_till_layer_n(in_pc, vcoeffs, last)
         if self.b_max_pool:
@@ -228,9 +231,12 @@ class MCEnc(nn.Module):
         head = self.layer_lst[last]
         # mu and std heads share input, table and coefficients: one gather/contract, two basis GEMMs
         z = F_.gather_contract(h, vcoeffs.vcoeffs_list[last], head.tables(h.device))
-        mu = head.forward_from_z(z, h, is_final_layer=True) * 0.1
-        std = self.stdlayer.forward_from_z(z, h, is_final_layer=True) * 0.01
-        return mu, std
+        return (head.forward_from_z(z, h, is_final_layer=True),
+                self.stdlayer.forward_from_z(z, h, is_final_layer=True))
+
+    def forward(self, in_pc, vcoeffs):
+        mu, std = self.forward_raw(in_pc, vcoeffs)
+        return mu * self.MU_SCALE, std * self.LOGSTD_SCALE
 
 
 class MCDec(nn.Module):
@@ -330,15 +336,18 @@ class MCLoss(nn.Module):
     def forward(self):
         return
 
-    def _laplacian(self, pc):
-        dev = pc.device
+    def tables(self, dev):
+        """Device tables of the layer-0 (Laplacian) connectivity."""
         if dev.type != "cuda":
             raise RuntimeError("MCLoss runs on CUDA only (no CPU fallback)")
         key = dev.index if dev.index is not None else torch.cuda.current_device()
         t = self._tables.get(key)
         if t is None:
             t = self._tables[key] = DeviceTables(self._table_host, self._table_host.shape[0], torch.device("cuda", key))
-        return F_.gather_contract(pc, self._lap_coeffs, t)          # [B, P, 3]
+        return t
+
+    def _laplacian(self, pc):
+        return F_.gather_contract(pc, self._lap_coeffs, self.tables(pc.device))          # [B, P, 3]
 
     def compute_geometric_loss_l1(self, gt_pc, predict_pc, weights=[]):
         if len(weights) == 0:

@@ -78,8 +78,26 @@ class Net_autoenc(nn.Module):
         self.w_nor = 10.0
         self.write_tmp_folder = getattr(param, "write_tmp_folder", "")
 
-    def losses(self, in_pc_batch, t_nor, t_eps=None):
-        """graphVAE_train.py:199-225. `t_eps` lets a caller fix the N(0,1) draw."""
+    def losses(self, in_pc_batch, t_nor, t_eps=None, fused=None):
+        """graphVAE_train.py:199-225. `t_eps` lets a caller fix the N(0,1) draw. `fused` (default: on, env
+        VCM_FUSED_LOSS=0 turns it off) runs the reparameterisation + KL and the three geometric losses as the
+        library's loss-head kernels (4 launches forward, 2 backward) instead of ~110 ATen elementwise / reduction
+        kernels around the M = 1 gathers; both paths compute the same quantities."""
+        if fused is None:
+            fused = os.environ.get("VCM_FUSED_LOSS", "1") == "1"
+        if fused and in_pc_batch.shape[2] == 3:
+            enc = self.net_geoenc
+            raw_mu, raw_logstd = enc.forward_raw(in_pc_batch, self.mcvcoeffsenc)
+            if t_eps is None:
+                t_eps = torch.empty_like(raw_mu).normal_()
+            t_z, klloss = F_.reparam_kl(raw_mu, raw_logstd, t_eps, enc.MU_SCALE, enc.LOGSTD_SCALE)
+            out_pc_batch = self.net_geodec(t_z, self.mcvcoeffsdec)[:, :, 0:3]
+            dev = in_pc_batch.device
+            geo, parts = F_.loss_head(out_pc_batch, in_pc_batch, t_nor, self.net_loss._lap_coeffs,
+                                      self.net_loss.tables(dev), self._face_tables_on(dev), self.w_pose,
+                                      self.w_laplace, self.w_nor)
+            loss = geo + klloss * self.klweight
+            return loss, parts[0], parts[1], klloss, parts[2], out_pc_batch
         t_mu, t_logstd = self.net_geoenc(in_pc_batch, self.mcvcoeffsenc)
         t_std = t_logstd.exp()
         if t_eps is None:
