@@ -211,6 +211,15 @@ VCM_API size_t vcm_basis_bwd_dz_workspace(int64_t rows, int M, int I, int O, int
 VCM_API int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, float *workspace, int64_t rows, int M,
                              int I, int O, int accumulate, int precision, void *stream);
 
+/* The stacked bases Wt[M*I, O] (Wt[m*I+i][o] = W[m][o][i]; the north_star's [M*in, out] matrix) depend on
+ * the parameters only, so a training step can build them once, off the backward chain (a second stream / a
+ * parallel graph branch), and hand them to K3: vcm_basis_bwd_dz_stacked is vcm_basis_bwd_dz without the
+ * in-call stacking. Valid where vcm_basis_bwd_dz_workspace() != 0 (tensor-core shapes), VCM_EUNSUPPORTED else;
+ * Wt has that many elements. */
+VCM_API int vcm_basis_stack(const float *W, float *Wt, int M, int I, int O, void *stream);
+VCM_API int vcm_basis_bwd_dz_stacked(const float *ds, const float *Wt, float *dz, int64_t rows, int M, int I,
+                                     int O, int precision, void *stream);
+
 /* K4: dW[m,o,i] = sum_r ds[r,o] * z[r,m,i]. workspace: fp32, at least
  * vcm_basis_bwd_dw_workspace() elements. Deterministic split reduction. */
 VCM_API size_t vcm_basis_bwd_dw_workspace(int64_t rows, int M, int I, int O, int precision);

@@ -55,6 +55,8 @@ SIGNATURES = {
     "vcm_colsum": (_i, [_p, _p, _i, _i, _p]),
     "vcm_basis_bwd_dz_workspace": (_sz, [_i64, _i, _i, _i, _i]),
     "vcm_basis_bwd_dz": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p]),
+    "vcm_basis_stack": (_i, [_p, _p, _i, _i, _i, _p]),
+    "vcm_basis_bwd_dz_stacked": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _p]),
     "vcm_basis_bwd_dw_workspace": (_sz, [_i64, _i, _i, _i, _i]),
     "vcm_basis_bwd_dw": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
     "vcm_adam_step": (_i, [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _i, _f, _p]),

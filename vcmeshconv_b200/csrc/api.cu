@@ -59,6 +59,23 @@ int vcm_basis_bwd_dz(const float *ds, const float *W, float *dz, float *workspac
     return simt_basis_bwd_dz(ds, W, dz, rows, M, I, O, accumulate, st);
 }
 
+int vcm_basis_stack(const float *W, float *Wt, int M, int I, int O, void *stream) {
+    VCM_CHECK(M > 0 && I > 0 && O > 0, "bad shape M=%d I=%d O=%d", M, I, O);
+    VCM_DEVPTR(W); VCM_DEVPTR(Wt);
+    return tc_stack_bases(W, Wt, M, I, O, (cudaStream_t)stream);
+}
+
+int vcm_basis_bwd_dz_stacked(const float *ds, const float *Wt, float *dz, int64_t rows, int M, int I, int O,
+                             int precision, void *stream) {
+    if (int e = check_gemm(rows, M, I, O, precision)) return e;
+    VCM_DEVPTR(ds); VCM_DEVPTR(Wt); VCM_DEVPTR(dz);
+    if (rows == 0) return VCM_OK;
+    if (precision == VCM_PREC_FP32 || !tc_supported(TC_DZ, rows, M, I, O, precision))
+        return fail(VCM_EUNSUPPORTED, "stacked bases are the tensor-core dz operand; this shape/precision runs "
+                                      "vcm_basis_bwd_dz (vcm_basis_bwd_dz_workspace() == 0)");
+    return tc_basis_bwd_dz(ds, nullptr, dz, const_cast<float *>(Wt), rows, M, I, O, 0, precision, (cudaStream_t)stream);
+}
+
 size_t vcm_basis_bwd_dw_workspace(int64_t rows, int M, int I, int O, int precision) {
     if (rows <= 0 || M <= 0 || I <= 0 || O <= 0) return 0;
     size_t a = simt_basis_bwd_dw_workspace(rows, M, I, O);

@@ -22,6 +22,7 @@ int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_poin
                  float *out, float *ws, int64_t R, int P_out, int M, int I, int O, int act, float sy, float sr,
                  int precision, cudaStream_t st);
 size_t tc_basis_bwd_dz_workspace(int M, int I, int O);
+int tc_stack_bases(const float *W, float *Wt, int M, int I, int O, cudaStream_t st);
 int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64_t R, int M, int I, int O,
                     int accumulate, int precision, cudaStream_t st);
 int reduce_dw_partials(const float *part, float *dW, int K, int O, int I, int n_split, cudaStream_t st);

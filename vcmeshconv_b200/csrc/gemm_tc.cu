@@ -467,14 +467,20 @@ int tc_basis_fwd(const float *z, const float *W, const float *bias, int per_poin
 
 size_t tc_basis_bwd_dz_workspace(int M, int I, int O) { return (size_t)M * I * O; }
 
+int tc_stack_bases(const float *W, float *Wt, int M, int I, int O, cudaStream_t st) {
+    dim3 tg((unsigned)ceil_div(I, 32), (unsigned)ceil_div(O, 32), (unsigned)M);
+    transpose_bases_kernel<<<tg, 256, 0, st>>>(W, Wt, M, I, O);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
 int tc_basis_bwd_dz(const float *ds, const float *W, float *dz, float *ws, int64_t R, int M, int I, int O,
                     int accumulate, int precision, cudaStream_t st) {
     if (accumulate) return fail(VCM_EUNSUPPORTED, "tensor-core dz does not accumulate");
     const int K = M * I, bn = pick_bn(K);
-    // stacked bases Wt[K][O]
-    dim3 tg((unsigned)ceil_div(I, 32), (unsigned)ceil_div(O, 32), (unsigned)M);
-    transpose_bases_kernel<<<tg, 256, 0, st>>>(W, ws, M, I, O);
-    VCM_LAUNCH_CHECK();
+    // stacked bases Wt[K][O]: built here, or already in `ws` when W is NULL (vcm_basis_bwd_dz_stacked)
+    if (W != nullptr)
+        if (int e = tc_stack_bases(W, ws, M, I, O, st)) return e;
     CUtensorMap ma, mb;
     {
         const uint64_t d[2] = {(uint64_t)O, (uint64_t)R}, s[2] = {4, (uint64_t)O * 4};

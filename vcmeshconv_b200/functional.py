@@ -115,15 +115,31 @@ def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
     dA = (dA_target if direct_dA else torch.empty_like(A)) if need_dA else None
     dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
     n_ws = L.vcm_coeff_grad_workspace_ex(t.handle, B, I, M, precision) if need_dA else 0
-    ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
+    split = need_dx and direct_dA and _da_stream is not None
+    ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws and not split else None
     st = _lib.stream_ptr()
     nnz, tag = t.nnz, "P%d>%d I%d M%d" % (p_in, t.p_out, I, M)
     gb = 4 * B * nnz * I
-    _lib.call("vcm_coeff_grad_ex", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M,
-              precision, st,
-              nbytes=4 * (dz.numel() + (x.numel() if need_dA else 0) + (2 if need_dA else 1) * nnz * M + nnz) +
-              (gb if need_dx else 0),
-              flops=2 * (int(need_dx) + int(need_dA)) * B * nnz * M * I, tag=tag)
+    if split:
+        # Only dG is on the backward chain (dG -> K6 -> dx -> next layer); dA goes straight into the flat gradient
+        # buffer and nothing downstream reads it. Two launches of K5 (compile-time dG-only / dA-only variants): the
+        # chain waits for the cheaper half, the dA half runs as a parallel branch next to it (dz is read twice).
+        _lib.call("vcm_coeff_grad_ex", t.handle, _ptr(dz), _ptr(x), _ptr(A), None, _ptr(dG), None, B, I, M,
+                  precision, st, nbytes=4 * (dz.numel() + nnz * M + nnz) + gb, flops=2 * B * nnz * M * I, tag=tag)
+        cur = torch.cuda.current_stream()
+        _da_stream.wait_stream(cur)
+        with torch.cuda.stream(_da_stream):
+            ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws else None
+            _lib.call("vcm_coeff_grad_ex", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), None, _ptr(ws), B, I, M,
+                      precision, _lib.stream_ptr(), nbytes=4 * (dz.numel() + x.numel() + 2 * nnz * M + nnz),
+                      flops=2 * B * nnz * M * I, tag=tag)
+        _side_keep.append((dz, x, ws))
+    else:
+        _lib.call("vcm_coeff_grad_ex", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M,
+                  precision, st,
+                  nbytes=4 * (dz.numel() + (x.numel() if need_dA else 0) + (2 if need_dA else 1) * nnz * M + nnz) +
+                  (gb if need_dx else 0),
+                  flops=2 * (int(need_dx) + int(need_dA)) * B * nnz * M * I, tag=tag)
     dx = None
     if need_dx:
         dx = torch.empty_like(x)
@@ -207,6 +223,16 @@ class _BasisGemm(torch.autograd.Function):
         ctx.cfg = (M, I, O, int(act), scale_y, scale_res, precision, per_point, bias is not None, res is not None)
         ctx.dW_target = _grad_target(W) if W.requires_grad else None
         ctx.db_target = _grad_target(bias) if bias is not None and bias.requires_grad else None
+        ctx.Wt = None
+        if _prep_stream is not None and ctx.needs_input_grad[0] and B and p_out:
+            # the dz GEMM's stacked-bases operand depends on W only: built now, on the trainer's preparation
+            # stream (a parallel branch from the start of the step), instead of in front of K3 on the backward chain
+            n_wt = _lib.lib().vcm_basis_bwd_dz_workspace(B * p_out, M, I, O, precision)
+            if n_wt:
+                with torch.cuda.stream(_prep_stream):
+                    ctx.Wt = torch.empty(n_wt, device=z.device, dtype=torch.float32)
+                    _lib.call("vcm_basis_stack", _ptr(W), _ptr(ctx.Wt), M, I, O, _lib.stream_ptr(),
+                              nbytes=8 * W.numel(), flops=0, tag="M%d I%d O%d" % (M, I, O))
         return out
 
     @staticmethod
@@ -215,10 +241,10 @@ class _BasisGemm(torch.autograd.Function):
         has_bias, has_res = ctx.cfg[8], ctx.cfg[9]
         need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2],
                 has_res and ctx.needs_input_grad[3])
-        return _basis_backward(z, W, y, dout, ctx.cfg, need, ctx.dW_target, ctx.db_target) + (None,) * 7
+        return _basis_backward(z, W, y, dout, ctx.cfg, need, ctx.dW_target, ctx.db_target, ctx.Wt) + (None,) * 7
 
 
-def _basis_backward(z, W, y, dout, cfg, need, dW_target, db_target):
+def _basis_backward(z, W, y, dout, cfg, need, dW_target, db_target, Wt=None):
     """act_bwd + K3 + K4: (dz, dW, dbias, dres) of out = basis_gemm(z, W, bias, res); gradients written into a
     `*_target` come back as None."""
     M, I, O, act, sy, sr, precision, per_point, has_bias, has_res = cfg
@@ -257,10 +283,14 @@ def _basis_backward(z, W, y, dout, cfg, need, dW_target, db_target):
     dz = dW = None
     if need_dz:
         dz = torch.empty_like(z)
-        n_ws = L.vcm_basis_bwd_dz_workspace(R, M, I, O, precision)
-        ws = torch.empty(n_ws, device=dev, dtype=torch.float32) if n_ws else None
-        _lib.call("vcm_basis_bwd_dz", _ptr(ds), _ptr(W), _ptr(dz), _ptr(ws), R, M, I, O, 0, precision, st,
-                  nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
+        if Wt is not None:                       # stacked bases prepared during the forward pass
+            _lib.call("vcm_basis_bwd_dz_stacked", _ptr(ds), _ptr(Wt), _ptr(dz), R, M, I, O, precision, st,
+                      nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
+        else:
+            n_ws = L.vcm_basis_bwd_dz_workspace(R, M, I, O, precision)
+            ws = torch.empty(n_ws, device=dev, dtype=torch.float32) if n_ws else None
+            _lib.call("vcm_basis_bwd_dz", _ptr(ds), _ptr(W), _ptr(dz), _ptr(ws), R, M, I, O, 0, precision, st,
+                      nbytes=4 * (ny + W.numel() + z.numel()), flops=2 * R * K * O, tag=tag)
     if need_dW:
         direct_dW = dW_target is not None
         dW = dW_target if direct_dW else torch.empty_like(W)
@@ -294,6 +324,25 @@ def set_side_stream(stream):
     _side_stream = stream
 
 
+# Optional preparation stream: work that depends on the parameters only (the stacked bases of the dz GEMMs). The
+# trainer forks it from the main stream at the start of a step and joins it before the backward pass.
+_prep_stream = None
+
+
+def set_prep_stream(stream):
+    global _prep_stream
+    _prep_stream = stream
+
+
+# Optional stream for the dA half of K5 (see _gather_backward); joined together with the dW stream.
+_da_stream = None
+
+
+def set_da_stream(stream):
+    global _da_stream
+    _da_stream = stream
+
+
 # Optional stream for the residual branch of every layer (forward; autograd replays a node's backward on the
 # stream of its forward, so the branch's backward overlaps the main chain as well). Set by the trainer.
 _residual_stream = None
@@ -310,8 +359,9 @@ def residual_stream():
 
 def join_side_stream():
     """The current stream waits for the branch; buffers parked for it are released."""
-    if _side_stream is not None:
-        torch.cuda.current_stream().wait_stream(_side_stream)
+    for st in (_side_stream, _da_stream):
+        if st is not None:
+            torch.cuda.current_stream().wait_stream(st)
     _side_keep.clear()
 
 

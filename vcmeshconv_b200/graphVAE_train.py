@@ -199,6 +199,13 @@ class DataParallelTrainer:
         # dW GEMMs on a second stream (parallel graph branch); VCM_DW_STREAM=0 turns it off
         self.dw_stream = (torch.cuda.Stream(self.flat.flat_p.device)
                           if self.flat.flat_p.is_cuda and os.environ.get("VCM_DW_STREAM", "1") == "1" else None)
+        # parameter-only preparation (stacked bases of the dz GEMMs) as a branch from the start of the step
+        self.prep_stream = (torch.cuda.Stream(self.flat.flat_p.device)
+                            if self.flat.flat_p.is_cuda and os.environ.get("VCM_PREP_STREAM", "1") == "1" else None)
+        # opt-in (VCM_SPLIT_K5=1): the dA half of K5 as a parallel branch. Measured slower on C2 (2.75 vs 2.63 ms):
+        # dz is read twice and the extra kernels slow the chain kernels they run next to.
+        self.da_stream = (torch.cuda.Stream(self.flat.flat_p.device)
+                          if self.flat.flat_p.is_cuda and os.environ.get("VCM_SPLIT_K5", "0") == "1" else None)
         # residual branch of every layer on its own stream (forward, and through autograd its backward)
         self.res_stream = (torch.cuda.Stream(self.flat.flat_p.device)
                            if self.flat.flat_p.is_cuda and os.environ.get("VCM_RES_STREAM", "1") == "1" else None)
@@ -265,17 +272,25 @@ class DataParallelTrainer:
         F_.begin_step(self.flat.params)
         if self.res_stream is not None and not self.overlap:
             F_.set_residual_stream(self.res_stream)
+        if self.prep_stream is not None:
+            self.prep_stream.wait_stream(torch.cuda.current_stream())
+            F_.set_prep_stream(self.prep_stream)
         try:
             loss, l1, lap, kl, lnor, _ = self.model.losses(pc, nor, eps)
         finally:
             F_.set_residual_stream(None)
-        if self.dw_stream is not None and not self.overlap:
+            F_.set_prep_stream(None)
+            if self.prep_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.prep_stream)
+        if not self.overlap:
             F_.set_side_stream(self.dw_stream)
+            F_.set_da_stream(self.da_stream)
         try:
             loss.backward()
         finally:
             F_.join_side_stream()
             F_.set_side_stream(None)
+            F_.set_da_stream(None)
         return loss.detach(), (l1.detach(), lap.detach(), kl.detach(), lnor.detach())
 
     @property
@@ -348,11 +363,20 @@ class DataParallelTrainer:
         self.overlap = False                         # no NCCL launches inside the capture
         self._set_direct_grads(True)
         self.static_pc, self.static_nor = pc.clone(), nor.clone()
+        # the N(0,1) draw of the reparameterisation (graphVAE_train.py:201) stays outside the graph: one normal_()
+        # launch in front of every replay, from torch's generator, instead of a captured generator (whose replay
+        # costs two extra fill kernels for seed and offset)
+        self.static_eps = None
+        if os.environ.get("VCM_EPS_OUTSIDE", "1") == "1":
+            m = self.model
+            self.static_eps = torch.empty(pc.shape[0], m.nrpt_latent, m.net_geoenc.out_nrchs, device=pc.device)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.forward_backward(self.static_pc, self.static_nor)
+                if self.static_eps is not None:
+                    self.static_eps.normal_()
+                self.forward_backward(self.static_pc, self.static_nor, self.static_eps)
                 self._finish_reduction()
                 self.optimizer_step()
         torch.cuda.current_stream().wait_stream(side)
@@ -360,7 +384,8 @@ class DataParallelTrainer:
         l0 = _lib.lib().vcm_launch_count()
         g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_fb, capture_error_mode="relaxed"):
-            self.static_loss, self.static_parts = self.forward_backward(self.static_pc, self.static_nor)
+            self.static_loss, self.static_parts = self.forward_backward(self.static_pc, self.static_nor,
+                                                                        self.static_eps)
             if self.world == 1:
                 self.optimizer_step()
         g_opt = None
@@ -378,6 +403,8 @@ class DataParallelTrainer:
         if nor.data_ptr() != self.static_nor.data_ptr():
             self.static_nor.copy_(nor, non_blocking=True)
         g_fb, g_opt = self._graph
+        if self.static_eps is not None:
+            self.static_eps.normal_()
         g_fb.replay()
         if g_opt is not None:
             dist.all_reduce(self.flat.flat_g, op=dist.ReduceOp.SUM, group=self.group)
