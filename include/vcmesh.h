@@ -241,6 +241,12 @@ VCM_API int vcm_adam_step(float *p, const float *g, float *m, float *v, size_t n
  * by writing state[1]. */
 VCM_API int vcm_adam_step_graph(float *p, const float *g, float *m, float *v, size_t n, float *state, float beta1,
                                 float beta2, float eps, float grad_scale, void *stream);
+/* The two halves of vcm_adam_step_graph, so that one step can update the flat buffer range by range (a range
+ * whose gradients are final is updated while the rest of the backward pass still runs): advance the state once
+ * per step, then apply it to any number of disjoint ranges. */
+VCM_API int vcm_adam_advance(float *state, float beta1, float beta2, void *stream);
+VCM_API int vcm_adam_apply(float *p, const float *g, float *m, float *v, size_t n, const float *state, float beta1,
+                           float beta2, float eps, float grad_scale, void *stream);
 
 /* ------------------------------------------------------------- loss head --
  * The autoencoder's loss glue (GraphAutoEncoder/graphVAE_train.py:199-225) as four

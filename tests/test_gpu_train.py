@@ -199,3 +199,46 @@ def test_graph_captured_step_matches_eager():
     assert abs(tr.opt_state[1].item() - 5e-4) < 1e-9
     loss2, _ = tr.step(pc * 1.0, nor * 1.0)       # different buffers are copied into the static inputs
     assert np.isfinite(loss2.item())
+
+
+def test_early_decoder_update_is_bitwise_equivalent(monkeypatch):
+    """The decoder-side Adam update applied next to the encoder's backward pass (early stream, hook on the latent
+    code) gives bit-identical parameters to one Adam launch after the backward pass, eagerly and captured."""
+    results = []
+    for early, graph in (("0", False), ("1", False), ("1", True)):
+        monkeypatch.setenv("VCM_EARLY_UPDATE", early)
+        model, pc, nor = _small_model(3)
+        tr = T.DataParallelTrainer(model, lr=1e-3)
+        assert (tr.early_stream is not None) == (early == "1") and 0 < tr.early_split < tr.flat.total
+        eps = torch.randn(4, model.nrpt_latent, 8, device="cuda")
+        if graph:
+            monkeypatch.setenv("VCM_EPS_OUTSIDE", "1")
+            tr.capture(pc, nor, warmup=0)
+            for _ in range(3):
+                tr.static_eps.copy_(eps)
+                tr._graph[0].replay()
+        else:
+            for _ in range(3):
+                tr.step(pc, nor, eps)
+        torch.cuda.synchronize()
+        results.append((tr.flat.flat_p.clone(), tr.exp_avg.clone(), tr.step_count))
+    for p, m, n in results[1:]:
+        assert n == 3 and torch.equal(p, results[0][0]) and torch.equal(m, results[0][1])
+
+
+def test_adam_apply_ranges_equal_one_launch():
+    torch.manual_seed(0)
+    n = 10_000
+    g = torch.randn(n, device="cuda")
+    L, st = _lib.lib(), _lib.stream_ptr()
+    outs = []
+    for ranges in ([(0, n)], [(0, 4096), (4096, n)]):
+        p, m, v = torch.ones(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        state = torch.tensor([0.0, 1e-3, 0.0, 0.0], device="cuda")
+        for _ in range(2):
+            _lib.check(L.vcm_adam_advance(state.data_ptr(), 0.9, 0.999, st))
+            for lo, hi in ranges:
+                _lib.check(L.vcm_adam_apply(p.data_ptr() + 4 * lo, g.data_ptr() + 4 * lo, m.data_ptr() + 4 * lo,
+                                            v.data_ptr() + 4 * lo, hi - lo, state.data_ptr(), 0.9, 0.999, 1e-8, 1.0, st))
+        outs.append((p, state.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1][0].item() == 2.0

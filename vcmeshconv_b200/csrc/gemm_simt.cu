@@ -505,12 +505,23 @@ __global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__
 }
 }  // namespace vcm
 
+extern "C" int vcm_adam_advance(float *state, float beta1, float beta2, void *stream) {
+    VCM_DEVPTR(state);
+    vcm::adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
 extern "C" int vcm_adam_step_graph(float *p, const float *g, float *m, float *v, size_t n, float *state, float beta1,
                                    float beta2, float eps, float grad_scale, void *stream) {
+    if (int e = vcm_adam_advance(state, beta1, beta2, stream)) return e;
+    return vcm_adam_apply(p, g, m, v, n, state, beta1, beta2, eps, grad_scale, stream);
+}
+
+extern "C" int vcm_adam_apply(float *p, const float *g, float *m, float *v, size_t n, const float *state, float beta1,
+                              float beta2, float eps, float grad_scale, void *stream) {
     VCM_DEVPTR(p); VCM_DEVPTR(g); VCM_DEVPTR(m); VCM_DEVPTR(v); VCM_DEVPTR(state);
     cudaStream_t st = (cudaStream_t)stream;
-    vcm::adam_advance_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
-    VCM_LAUNCH_CHECK();
     if (n == 0) return VCM_OK;
     int64_t blocks = vcm::ceil_div((int64_t)n, 256 * 4);
     const int64_t cap = (int64_t)vcm::sm_count() * 8;

@@ -222,7 +222,10 @@ using namespace vcm;
 
 extern "C" {
 
-size_t vcm_reparam_kl_workspace(size_t n) { return n > 1024 * 64 ? (size_t)sm_count() : 0; }
+// one 1024-thread CTA per 4096 elements (a single CTA walking a 50k-element latent takes 26 us), at most one per SM
+static int reparam_grid(size_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)n, 4096), sm_count())); }
+
+size_t vcm_reparam_kl_workspace(size_t n) { return reparam_grid(n) > 1 ? (size_t)reparam_grid(n) : 0; }
 
 int vcm_reparam_kl_fwd(const float *raw_mu, const float *raw_logstd, const float *eps, float *z, float *kl,
                        float *workspace, size_t n, float scale_mu, float scale_logstd, void *stream) {
@@ -230,7 +233,7 @@ int vcm_reparam_kl_fwd(const float *raw_mu, const float *raw_logstd, const float
     VCM_DEVPTR(raw_mu); VCM_DEVPTR(raw_logstd); VCM_DEVPTR(eps); VCM_DEVPTR(z); VCM_DEVPTR(kl);
     VCM_DEVPTR_OPT(workspace);
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = vcm_reparam_kl_workspace(n) ? sm_count() : 1;
+    const int grid = reparam_grid(n);
     VCM_CHECK(grid == 1 || workspace != nullptr, "workspace required (%d partial sums)", grid);
     reparam_kl_fwd_kernel<<<grid, 1024, 0, st>>>(raw_mu, raw_logstd, eps, z, workspace, kl, n, scale_mu, scale_logstd);
     VCM_LAUNCH_CHECK();

@@ -178,9 +178,24 @@ class _ProjectGather(torch.autograd.Function):
         dA = (ctx.dA_target if direct else torch.empty_like(A)) if need_dA else None
         du = torch.empty_like(u) if need_du else None
         nnz = t.nnz
-        _lib.call("vcm_project_gather_bwd", t.handle, _ptr(ds), _ptr(u), _ptr(A), _ptr(dA), _ptr(du), B, M, O,
-                  _lib.stream_ptr(), nbytes=4 * (B * nnz * M * O + 2 * nnz * M + ds.numel() + (du.numel() if need_du else 0)),
-                  flops=2 * (int(need_du) + int(need_dA)) * B * nnz * M * O, tag="P%d>%d MO%d" % (t.p_in, t.p_out, M * O))
+        tag = "P%d>%d MO%d" % (t.p_in, t.p_out, M * O)
+        if direct and need_du and _side_stream is not None:
+            # du feeds the rest of the backward pass, dA goes straight into the flat gradient buffer: the dA kernel
+            # runs next to the chain on the side stream (the C call launches one kernel per requested gradient)
+            _lib.call("vcm_project_gather_bwd", t.handle, _ptr(ds), _ptr(u), _ptr(A), None, _ptr(du), B, M, O,
+                      _lib.stream_ptr(), nbytes=4 * (B * nnz * M * O + nnz * M + ds.numel() + du.numel()),
+                      flops=2 * B * nnz * M * O, tag=tag)
+            _side_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(_side_stream):
+                _lib.call("vcm_project_gather_bwd", t.handle, _ptr(ds), _ptr(u), _ptr(A), _ptr(dA), None, B, M, O,
+                          _lib.stream_ptr(), nbytes=4 * (B * nnz * M * O + 2 * nnz * M + ds.numel()),
+                          flops=2 * B * nnz * M * O, tag=tag)
+            _side_keep.append((ds, u))
+        else:
+            _lib.call("vcm_project_gather_bwd", t.handle, _ptr(ds), _ptr(u), _ptr(A), _ptr(dA), _ptr(du), B, M, O,
+                      _lib.stream_ptr(),
+                      nbytes=4 * (B * nnz * M * O + 2 * nnz * M + ds.numel() + (du.numel() if need_du else 0)),
+                      flops=2 * (int(need_du) + int(need_dA)) * B * nnz * M * O, tag=tag)
         return du, (None if direct or not need_dA else dA), None, None, None
 
 

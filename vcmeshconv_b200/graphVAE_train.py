@@ -77,6 +77,10 @@ class Net_autoenc(nn.Module):
         self.klweight = 1e-5
         self.w_nor = 10.0
         self.write_tmp_folder = getattr(param, "write_tmp_folder", "")
+        # called with d loss / d latent when the decoder's backward pass is complete (set by the trainer: from
+        # that moment the decoder-side gradients are final and can be reduced / applied while the encoder's
+        # backward pass still runs)
+        self.latent_grad_hook = None
 
     def losses(self, in_pc_batch, t_nor, t_eps=None, fused=None):
         """graphVAE_train.py:199-225. `t_eps` lets a caller fix the N(0,1) draw. `fused` (default: on, env
@@ -91,6 +95,8 @@ class Net_autoenc(nn.Module):
             if t_eps is None:
                 t_eps = torch.empty_like(raw_mu).normal_()
             t_z, klloss = F_.reparam_kl(raw_mu, raw_logstd, t_eps, enc.MU_SCALE, enc.LOGSTD_SCALE)
+            if self.latent_grad_hook is not None and t_z.requires_grad:
+                t_z.register_hook(self.latent_grad_hook)
             out_pc_batch = self.net_geodec(t_z, self.mcvcoeffsdec)[:, :, 0:3]
             dev = in_pc_batch.device
             geo, parts = F_.loss_head(out_pc_batch, in_pc_batch, t_nor, self.net_loss._lap_coeffs,
@@ -103,6 +109,8 @@ class Net_autoenc(nn.Module):
         if t_eps is None:
             t_eps = torch.ones_like(t_std).normal_()
         t_z = t_mu + t_std * t_eps
+        if self.latent_grad_hook is not None and t_z.requires_grad:
+            t_z.register_hook(self.latent_grad_hook)
         klloss = torch.mean(-0.5 - t_logstd + 0.5 * t_mu ** 2 + 0.5 * torch.exp(2 * t_logstd))
         out_pc_batch = self.net_geodec(t_z, self.mcvcoeffsdec)[:, :, 0:3]
         dif_pos = out_pc_batch - in_pc_batch
@@ -189,7 +197,11 @@ class DataParallelTrainer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
-        self.flat = FlatBuffers(model.trainable_parameters(), bucket_bytes)
+        # flat layout: decoder side (layers, then coefficients) first, encoder side after it, so that "everything
+        # whose gradient is final when the decoder's backward pass ends" is one contiguous range [0, early_split)
+        dec_side, enc_side = self._split_params(model)
+        self.flat = FlatBuffers(dec_side + enc_side, bucket_bytes)
+        self.early_split = (self.flat.offsets[len(dec_side)] if enc_side else self.flat.total) if dec_side else 0
         self.exp_avg = torch.zeros_like(self.flat.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat.flat_p)
         # optimizer scalars live on the device so a captured step can be replayed: {step, lr, 1-b1^t, sqrt(1-b2^t)}
@@ -209,6 +221,10 @@ class DataParallelTrainer:
         # residual branch of every layer on its own stream (forward, and through autograd its backward)
         self.res_stream = (torch.cuda.Stream(self.flat.flat_p.device)
                            if self.flat.flat_p.is_cuda and os.environ.get("VCM_RES_STREAM", "1") == "1" else None)
+        # decoder-side all-reduce + Adam next to the encoder's backward pass (VCM_EARLY_UPDATE=0 turns it off)
+        self.early_stream = (torch.cuda.Stream(self.flat.flat_p.device)
+                             if self.flat.flat_p.is_cuda and os.environ.get("VCM_EARLY_UPDATE", "1") == "1" else None)
+        self._advanced = self._early_done = False
         self.overlap = overlap and self.world > 1
         self._pending = []
         self._handles = []
@@ -217,6 +233,14 @@ class DataParallelTrainer:
         self._set_direct_grads(not self.overlap)
         if self.world > 1:
             self.broadcast_parameters()
+
+    @staticmethod
+    def _split_params(model):
+        params = model.trainable_parameters()
+        if not (hasattr(model, "net_geodec") and hasattr(model, "mcvcoeffsdec")):
+            return [], params
+        dec_ids = {id(p) for p in model.net_geodec.parameters()} | {id(p) for p in model.mcvcoeffsdec.parameters()}
+        return [p for p in params if id(p) in dec_ids], [p for p in params if id(p) not in dec_ids]
 
     # -- communication ------------------------------------------------------------
     def broadcast_parameters(self):
@@ -258,7 +282,9 @@ class DataParallelTrainer:
                 h.wait()
             self._handles = []
         else:
-            dist.all_reduce(self.flat.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            lo = self.early_split if self._early_done else 0           # [0, lo) was reduced next to the backward pass
+            if lo < self.flat.total:
+                dist.all_reduce(self.flat.flat_g[lo:], op=dist.ReduceOp.SUM, group=self.group)
 
     # -- one training step ---------------------------------------------------------
     def _set_direct_grads(self, on):
@@ -267,13 +293,23 @@ class DataParallelTrainer:
         for p in self.flat.params:
             p._vcm_grad_buf = p.grad if on else None
 
-    def forward_backward(self, pc, nor, eps=None):
+    def forward_backward(self, pc, nor, eps=None, early=False):
+        """zero_grad + forward + backward. With `early` (step() and the captured step use it) the decoder-side range
+        of the flat buffers is all-reduced and its Adam update applied on `early_stream` as soon as the decoder's
+        backward pass is complete, next to the encoder's backward pass; the caller finishes the step with
+        _finish_reduction() + optimizer_step(), which then only touch the rest."""
         self.flat.zero_grad()
         F_.begin_step(self.flat.params)
+        self._early_done = False
+        cur = torch.cuda.current_stream() if self.flat.flat_p.is_cuda else None
+        if early and self.early_stream is not None and self.early_split > 0 and not self.overlap:
+            self._advance()                              # this step's optimizer scalars, before anything applies them
+            self.early_stream.wait_stream(cur)
+            self.model.latent_grad_hook = self._decoder_backward_done
         if self.res_stream is not None and not self.overlap:
             F_.set_residual_stream(self.res_stream)
         if self.prep_stream is not None:
-            self.prep_stream.wait_stream(torch.cuda.current_stream())
+            self.prep_stream.wait_stream(cur)
             F_.set_prep_stream(self.prep_stream)
         try:
             loss, l1, lap, kl, lnor, _ = self.model.losses(pc, nor, eps)
@@ -281,7 +317,7 @@ class DataParallelTrainer:
             F_.set_residual_stream(None)
             F_.set_prep_stream(None)
             if self.prep_stream is not None:
-                torch.cuda.current_stream().wait_stream(self.prep_stream)
+                cur.wait_stream(self.prep_stream)
         if not self.overlap:
             F_.set_side_stream(self.dw_stream)
             F_.set_da_stream(self.da_stream)
@@ -291,7 +327,24 @@ class DataParallelTrainer:
             F_.join_side_stream()
             F_.set_side_stream(None)
             F_.set_da_stream(None)
+            if getattr(self.model, "latent_grad_hook", None) is not None:
+                self.model.latent_grad_hook = None
+                cur.wait_stream(self.early_stream)
         return loss.detach(), (l1.detach(), lap.detach(), kl.detach(), lnor.detach())
+
+    def _decoder_backward_done(self, grad):
+        """Tensor hook on the latent code: autograd runs nodes in reverse creation order, so when d loss / d latent
+        is complete every decoder-side backward kernel has been enqueued (on the chain or on a branch stream)."""
+        s = self.early_stream
+        s.wait_stream(torch.cuda.current_stream())
+        for st in (F_._side_stream, F_._da_stream, self.res_stream):
+            if st is not None:
+                s.wait_stream(st)
+        with torch.cuda.stream(s):
+            if self.world > 1:
+                dist.all_reduce(self.flat.flat_g[:self.early_split], op=dist.ReduceOp.SUM, group=self.group)
+            self._apply(0, self.early_split)
+        self._early_done = True
 
     @property
     def step_count(self):
@@ -302,18 +355,32 @@ class DataParallelTrainer:
         self.lr = lr
         self.opt_state[1] = lr
 
+    def _advance(self):
+        _lib.call("vcm_adam_advance", self.opt_state.data_ptr(), self.betas[0], self.betas[1], _lib.stream_ptr())
+        self._advanced = True
+
+    def _apply(self, lo, hi):
+        f = self.flat
+        if hi > lo:
+            o = 4 * lo
+            _lib.call("vcm_adam_apply", f.flat_p.data_ptr() + o, f.flat_g.data_ptr() + o, self.exp_avg.data_ptr() + o,
+                      self.exp_avg_sq.data_ptr() + o, hi - lo, self.opt_state.data_ptr(), self.betas[0], self.betas[1],
+                      self.eps, 1.0, _lib.stream_ptr(), nbytes=28 * (hi - lo), flops=12 * (hi - lo))
+
     def optimizer_step(self):
+        """Adam over the flat buffers (the part an early update has not already covered in this step)."""
         f = self.flat
         if not f.flat_p.is_cuda:
             raise RuntimeError("the optimizer step runs on CUDA only (no CPU fallback)")
-        _lib.call("vcm_adam_step_graph", f.flat_p.data_ptr(), f.flat_g.data_ptr(), self.exp_avg.data_ptr(),
-                  self.exp_avg_sq.data_ptr(), f.total, self.opt_state.data_ptr(), self.betas[0], self.betas[1],
-                  self.eps, 1.0, _lib.stream_ptr(), nbytes=28 * f.total, flops=12 * f.total)
+        if not self._advanced:
+            self._advance()
+        self._apply(self.early_split if self._early_done else 0, f.total)
+        self._advanced = self._early_done = False
 
     def step(self, pc, nor, eps=None):
         if self._graph is not None and eps is None:
             return self._graph_step(pc, nor)
-        loss, parts = self.forward_backward(pc, nor, eps)
+        loss, parts = self.forward_backward(pc, nor, eps, early=True)
         self._finish_reduction()
         self.optimizer_step()
         return loss, parts
@@ -354,11 +421,10 @@ class DataParallelTrainer:
 
     # -- CUDA-graph capture of the step -----------------------------------------------
     def capture(self, pc, nor, warmup=3):
-        """Captures zero_grad + forward + backward (+ Adam when there is no collective in
-        between) into CUDA graphs; tables and shapes are static, so every later
-        step() is one or two graph launches instead of ~300 kernel launches from
-        Python. With world_size > 1 the gradient all-reduce (NCCL) runs between
-        the two graphs on the same stream."""
+        """Captures the whole step (zero_grad, forward, backward, gradient all-reduce, Adam) into one CUDA
+        graph; tables and shapes are static, so every later step() is one graph launch instead of ~250 kernel
+        launches from Python. The captured graph has parallel branches: residual branches, dW GEMMs, the
+        stacked-bases preparation and the early decoder-side all-reduce + Adam."""
         assert pc.is_cuda and self._graph is None
         self.overlap = False                         # no NCCL launches inside the capture
         self._set_direct_grads(True)
@@ -376,20 +442,25 @@ class DataParallelTrainer:
             for _ in range(warmup):
                 if self.static_eps is not None:
                     self.static_eps.normal_()
-                self.forward_backward(self.static_pc, self.static_nor, self.static_eps)
+                self.forward_backward(self.static_pc, self.static_nor, self.static_eps, early=True)
                 self._finish_reduction()
                 self.optimizer_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         l0 = _lib.lib().vcm_launch_count()
+        # One graph for the whole step. With world_size > 1 the NCCL all-reduces are captured too (the decoder-side
+        # range on the early stream, the rest after the backward pass); VCM_GRAPH_NCCL=0 keeps NCCL out of the
+        # capture: graph(fwd + bwd) -> all-reduce -> graph(Adam).
+        nccl_in_graph = self.world == 1 or os.environ.get("VCM_GRAPH_NCCL", "1") == "1"
         g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_fb, capture_error_mode="relaxed"):
             self.static_loss, self.static_parts = self.forward_backward(self.static_pc, self.static_nor,
-                                                                        self.static_eps)
-            if self.world == 1:
+                                                                        self.static_eps, early=nccl_in_graph)
+            if nccl_in_graph:
+                self._finish_reduction()
                 self.optimizer_step()
         g_opt = None
-        if self.world > 1:
+        if not nccl_in_graph:
             g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_opt, capture_error_mode="relaxed"):
                 self.optimizer_step()
