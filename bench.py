@@ -184,6 +184,7 @@ def run_ours(args):
     from vcmeshconv_b200 import _lib, functional as F_
     from vcmeshconv_b200 import graphVAE_train as T
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's version banner must not land in front of the JSON line
     rank, local, world = T.init_distributed()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")

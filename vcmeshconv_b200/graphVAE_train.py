@@ -421,10 +421,10 @@ class DataParallelTrainer:
 
     # -- CUDA-graph capture of the step -----------------------------------------------
     def capture(self, pc, nor, warmup=3):
-        """Captures the whole step (zero_grad, forward, backward, gradient all-reduce, Adam) into one CUDA
-        graph; tables and shapes are static, so every later step() is one graph launch instead of ~250 kernel
-        launches from Python. The captured graph has parallel branches: residual branches, dW GEMMs, the
-        stacked-bases preparation and the early decoder-side all-reduce + Adam."""
+        """Captures the step into CUDA graphs; tables and shapes are static, so every later step() is one graph
+        launch (world_size 1: zero_grad, forward, backward, Adam) or two with the NCCL all-reduce between them,
+        instead of ~250 kernel launches from Python. The captured graph has parallel branches: residual branches,
+        dW GEMMs, the stacked-bases preparation and the early decoder-side Adam."""
         assert pc.is_cuda and self._graph is None
         self.overlap = False                         # no NCCL launches inside the capture
         self._set_direct_grads(True)
@@ -442,16 +442,17 @@ class DataParallelTrainer:
             for _ in range(warmup):
                 if self.static_eps is not None:
                     self.static_eps.normal_()
-                self.forward_backward(self.static_pc, self.static_nor, self.static_eps, early=True)
+                self.forward_backward(self.static_pc, self.static_nor, self.static_eps, early=self.world == 1)
                 self._finish_reduction()
                 self.optimizer_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         l0 = _lib.lib().vcm_launch_count()
-        # One graph for the whole step. With world_size > 1 the NCCL all-reduces are captured too (the decoder-side
-        # range on the early stream, the rest after the backward pass); VCM_GRAPH_NCCL=0 keeps NCCL out of the
-        # capture: graph(fwd + bwd) -> all-reduce -> graph(Adam).
-        nccl_in_graph = self.world == 1 or os.environ.get("VCM_GRAPH_NCCL", "1") == "1"
+        # world_size 1: one graph for the whole step. world_size > 1: graph(fwd + bwd) -> NCCL all-reduce of the flat
+        # gradient buffer -> graph(Adam). VCM_GRAPH_NCCL=1 captures the all-reduces as well (decoder-side range on
+        # the early stream, the rest after the backward pass; one graph per step) -- opt-in: with c10d's NCCL
+        # process group that capture hung on 2 x B200 in this image (torch 2.11 / NCCL 2.28), so it is not the default.
+        nccl_in_graph = self.world == 1 or os.environ.get("VCM_GRAPH_NCCL", "0") == "1"
         g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_fb, capture_error_mode="relaxed"):
             self.static_loss, self.static_parts = self.forward_backward(self.static_pc, self.static_nor,
