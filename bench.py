@@ -301,9 +301,16 @@ def run_ours(args):
     if not args.no_profile:
         # per-kernel events need eager launches: same kernels, same stream, launched one by one. Every rank
         # runs the pass (the step contains the gradient all-reduce); rank 0 reports.
+        # one stream, so that every call's event pair brackets that call's kernels alone
         g, trainer._graph = trainer._graph, None
+        branches = ("dw_stream", "res_stream", "prep_stream", "early_stream", "da_stream")
+        saved = {k: getattr(trainer, k) for k in branches}
+        for k in branches:
+            setattr(trainer, k, None)
         roof, breakdown = roofline(trainer, resident, n_rot, min(args.steps, 5),
                                    args.breakdown_file if rank == 0 else "")
+        for k, st in saved.items():
+            setattr(trainer, k, st)
         trainer._graph = g
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,9 +350,9 @@ def run_ours(args):
 
 def roofline(trainer, resident, n_rot, steps, dump=""):
     """Per-entry-point CUDA-event timing of `steps` further training steps
-    (events on the launching stream). The dominant entry point's algorithmic
-    bytes (SURVEY §8d formulas, counted per call in functional.py) over its
-    summed duration is `achieved`."""
+    (events on the launching stream). `achieved` = algorithmic bytes (SURVEY
+    §8d formulas, counted per call in functional.py) of the dominant kernel
+    (entry point x layer shape) over its summed duration."""
     import torch
     from vcmeshconv_b200 import _lib
     peaks = {}
@@ -378,25 +385,36 @@ def roofline(trainer, resident, n_rot, steps, dump=""):
                  for k, v in summ.items()}
     top = max(summ, key=lambda k: summ[k]["ms"])
     v = summ[top]
-    achieved = v["bytes"] / v["ms"] / 1e6                      # GB/s
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/traffic_r1.json):
-    # measured dram bytes / algorithmic bytes of the profiled launch, applied to this run's per-launch average
+    # The dominant KERNEL is one instantiation on one layer shape: the (entry point, shape) pair with the largest
+    # summed time. The entry point's other shapes run different kernels (tensor-pipe / fp32 / M = 1 variants) on
+    # layers as small as 51 vertices, where a launch is latency-bound; their aggregate is reported next to it.
+    shape = max(v["by_tag"], key=lambda t: v["by_tag"][t]["ms"])
+    sv = v["by_tag"][shape]
+    achieved = sv["bytes"] / sv["ms"] / 1e6                    # GB/s
+    agg = v["bytes"] / v["ms"] / 1e6
+    # DRAM traffic of that kernel from the committed ncu --set full capture of the same layer shape
+    # (profiles/traffic_r1.json): measured dram bytes per launch
     traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-        if tr["kernel"] in (top, top[:-3] if top.endswith("_ex") else top):
-            traffic = tr["ratio"] * v["bytes"] / v["calls"]
+        if tr["kernel"] in (top, top[:-3] if top.endswith("_ex") else top) and tr.get("shape") == shape:
+            traffic = tr["dram_bytes"]
             traffic_src = "%s: %.1f MB measured vs %.1f MB algorithmic on %s" % (
                 tr["source"], tr["dram_bytes"] / 1e6, tr["algorithmic_bytes"] / 1e6, tr["layer"])
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "%s [%s]" % (top, shape), "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
-            "launches": v["calls"], "avg_launch_ms": v["ms"] / v["calls"],
-            "algorithmic_bytes_per_launch": v["bytes"] / v["calls"],
-            "how": "CUDA events around every call of this entry point on the launching stream, over %d steps "
-                   "run right after the timed region" % steps}
+            "launches": sv["calls"], "avg_launch_ms": sv["ms"] / sv["calls"],
+            "algorithmic_bytes_per_launch": sv["bytes"] / sv["calls"],
+            "share_of_step": sv["ms"] / total,
+            "entry_point_all_shapes": {"achieved": agg, "frac": agg / peak, "launches": v["calls"],
+                                       "avg_launch_ms": v["ms"] / v["calls"], "share_of_step": v["ms"] / total,
+                                       "algorithmic_bytes_per_launch": v["bytes"] / v["calls"]},
+            "how": "CUDA events around every call of this entry point on the launching stream, over %d eager steps "
+                   "run right after the timed region (per-call times include launch gaps the graph replay hides)"
+                   % steps}
     return roof, breakdown
 
 
