@@ -383,38 +383,46 @@ def roofline(trainer, resident, n_rot, steps, dump=""):
                               "TFLOPs": tv["flops"] / tv["ms"] / 1e9 if tv["ms"] else None}
                              for t, tv in sorted(v["by_tag"].items(), key=lambda kv: -kv[1]["ms"])[:4]]}
                  for k, v in summ.items()}
+    # The dominant KERNEL: the entry point with the largest summed time, and inside it the kernel that carries most of
+    # that time (functional.py tags the K5 calls "mma" = tensor-pipe kernel / "fp32" = CUDA-core kernel,
+    # include/vcmesh.h vcm_coeff_grad_variant), over ALL the layer shapes that kernel was launched on.
     top = max(summ, key=lambda k: summ[k]["ms"])
-    v = summ[top]
-    # The dominant KERNEL is one instantiation on one layer shape: the (entry point, shape) pair with the largest
-    # summed time. The entry point's other shapes run different kernels (tensor-pipe / fp32 / M = 1 variants) on
-    # layers as small as 51 vertices, where a launch is latency-bound; their aggregate is reported next to it.
-    shape = max(v["by_tag"], key=lambda t: v["by_tag"][t]["ms"])
-    sv = v["by_tag"][shape]
-    achieved = sv["bytes"] / sv["ms"] / 1e6                    # GB/s
-    agg = v["bytes"] / v["ms"] / 1e6
-    # DRAM traffic of that kernel from the committed ncu --set full capture of the same layer shape
-    # (profiles/traffic_r1.json): measured dram bytes per launch
+    groups = {}
+    for tag, tv in summ[top]["by_tag"].items():
+        var = tag.split()[-1] if tag.split() and tag.split()[-1] in ("mma", "fp32") else ""
+        g = groups.setdefault(var, {"ms": 0.0, "bytes": 0, "calls": 0, "shapes": {}})
+        g["ms"] += tv["ms"]; g["bytes"] += tv["bytes"]; g["calls"] += tv["calls"]
+        g["shapes"][tag] = tv
+    var, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    achieved = g["bytes"] / g["ms"] / 1e6                      # GB/s
+    shapes = [{"shape": t, "share_of_step": tv["ms"] / total, "avg_launch_ms": tv["ms"] / tv["calls"],
+               "algorithmic_bytes_per_launch": tv["bytes"] / tv["calls"], "achieved": tv["bytes"] / tv["ms"] / 1e6,
+               "frac": tv["bytes"] / tv["ms"] / 1e6 / peak}
+              for t, tv in sorted(g["shapes"].items(), key=lambda kv: -kv[1]["ms"])]
+    # DRAM traffic: measured / algorithmic bytes of the committed ncu --set full capture of this kernel on one of
+    # these shapes (profiles/traffic_r1.json), applied to this run's average algorithmic bytes per launch
     traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-        if tr["kernel"] in (top, top[:-3] if top.endswith("_ex") else top) and tr.get("shape") == shape:
-            traffic = tr["dram_bytes"]
+        if tr["kernel"] in (top, top[:-3] if top.endswith("_ex") else top) and any(
+                t.startswith(tr["shape"]) for t in g["shapes"]):
+            traffic = tr["ratio"] * g["bytes"] / g["calls"]
             traffic_src = "%s: %.1f MB measured vs %.1f MB algorithmic on %s" % (
                 tr["source"], tr["dram_bytes"] / 1e6, tr["algorithmic_bytes"] / 1e6, tr["layer"])
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": "%s [%s]" % (top, shape), "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+    roof = {"bound": "hbm", "kernel": top + (" (%s kernel)" % var if var else ""), "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
-            "launches": sv["calls"], "avg_launch_ms": sv["ms"] / sv["calls"],
-            "algorithmic_bytes_per_launch": sv["bytes"] / sv["calls"],
-            "share_of_step": sv["ms"] / total,
-            "entry_point_all_shapes": {"achieved": agg, "frac": agg / peak, "launches": v["calls"],
-                                       "avg_launch_ms": v["ms"] / v["calls"], "share_of_step": v["ms"] / total,
-                                       "algorithmic_bytes_per_launch": v["bytes"] / v["calls"]},
+            "launches": g["calls"], "avg_launch_ms": g["ms"] / g["calls"],
+            "algorithmic_bytes_per_launch": g["bytes"] / g["calls"], "share_of_step": g["ms"] / total,
+            "shapes": shapes[:4],
+            "entry_point_all_kernels": {"achieved": summ[top]["bytes"] / summ[top]["ms"] / 1e6,
+                                        "frac": summ[top]["bytes"] / summ[top]["ms"] / 1e6 / peak,
+                                        "launches": summ[top]["calls"], "share_of_step": summ[top]["ms"] / total},
             "how": "CUDA events around every call of this entry point on the launching stream, over %d eager steps "
-                   "run right after the timed region (per-call times include launch gaps the graph replay hides)"
-                   % steps}
+                   "on one stream right after the timed region; all launches of the kernel (%d layer shapes) summed; "
+                   "per-call times include launch gaps the graph replay hides" % (steps, len(shapes))}
     return roof, breakdown
 
 

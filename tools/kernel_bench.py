@@ -18,7 +18,7 @@ from vcmeshconv_b200 import synthetic
 # name: (table, level-in index, I, O)   on the 6890-vertex C2 hierarchy
 LAYERS = {"enc1": ("pool2", 2, 32, 64), "enc2": ("pool3", 3, 64, 128), "enc3": ("pool4", 4, 128, 256),
           "enc4": ("pool5", 5, 256, 512), "dec1": ("unpool5", 6, 512, 256), "dec2": ("unpool4", 5, 256, 128),
-          "dec3": ("unpool3", 4, 128, 64), "dec4": ("unpool2", 3, 64, 32)}
+          "dec3": ("unpool3", 4, 128, 64), "dec4": ("unpool2", 2, 64, 32)}
 
 
 def main():
@@ -33,7 +33,8 @@ def main():
     tabs, nums = gs.build_tables(faces, 6890, synthetic.alternating_levels(7))
     tname, lvl, I, O = LAYERS[a.layer]
     table = tabs[tname]
-    p_in = nums[lvl + 1] if tname.startswith("unpool") else nums[lvl]
+    mx = int(table[:, 1::2].max())                   # the padding sentinel is p_in itself; without padding max id = p_in - 1
+    p_in = mx if mx in nums else mx + 1
     t = connectivity.DeviceTables(table, p_in)
     B, M, P, N = a.batch, 17, t.p_out, t.n_max
     L, st = _lib.lib(), _lib.stream_ptr()

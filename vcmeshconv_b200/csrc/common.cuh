@@ -53,6 +53,7 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 // ---- device tables (owned by vcm_tables) -----------------------------------
 struct Tables {
     int32_t p_in = 0, p_out = 0, n_max = 0, max_last = 0, max_rev = 0, device = 0;
+    int32_t n_gt16 = 0;           // vertices with last > 16: slots [0, n_gt16) of the processing order (degree buckets)
     int64_t nnz = 0;
     int32_t *idx = nullptr;       // [p_out, n_max]
     int32_t *last = nullptr;      // [p_out]

@@ -1059,7 +1059,9 @@ __global__ void __launch_bounds__(128, NT16 <= 2 ? 4 : 3)
 coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__restrict__ meta_sorted,
                       const float *__restrict__ dz, const float *__restrict__ x, const float *__restrict__ A,
                       float *__restrict__ dA_out, float *__restrict__ dG, int p_in, int p_out, int n_max, int I, int M,
-                      int B, int tiles_per_cta) {
+                      int B, int tiles_per_cta, int slot0, int n_stage) {
+    // slot0 / n_stage: this launch covers the slots from slot0 on (one degree bucket of the processing order) and
+    // stages at most n_stage neighbour rows per tile (<= n_max, the row stride of the tables and of dA / dG)
     constexpr int NP = NT16 * 16;                                    // padded neighbour count
     constexpr bool KEEP = NT16 <= 2;                                 // coefficient fragments live in registers
     extern __shared__ __align__(16) float smem[];
@@ -1067,11 +1069,11 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
     float *Al_s = A_s + NP * kK5S;                                   // [NP][kK5S]  lo parts (X3 only)
     int32_t *idx_s = reinterpret_cast<int32_t *>(Al_s + (X3 ? NP * kK5S : 0));   // [NP], -1 = no neighbour
     float *zero_s = reinterpret_cast<float *>(idx_s + NP);           // [kTS] zeros
-    float *stage_s = zero_s + kTS;                                   // [4 warps][kNBuf][M + n_max][kTS]; part_s at the end
+    float *stage_s = zero_s + kTS;                                   // [4 warps][kNBuf][M + n_stage][kTS]; part_s at the end
     float *part_s = stage_s;                                         // [4 warps][NP][24]
-    const int buf_words = (M + n_max) * kTS, warp_words = kNBuf * buf_words;
+    const int buf_words = (M + n_stage) * kTS, warp_words = kNBuf * buf_words;
 
-    const int slot = blockIdx.x;
+    const int slot = blockIdx.x + slot0;
     const int2 meta = __ldg(meta_sorted + slot);
     const int p = meta.x, l = meta.y;
     const int tid = threadIdx.x;
@@ -1347,6 +1349,12 @@ coeff_grad_mma_kernel(const int32_t *__restrict__ idx_sorted, const int2 *__rest
 
 struct MmaGradPlan { int nt16, gy, tiles_per_cta; size_t smem; };
 
+static size_t grad_mma_smem(int nt16, int M, int n_stage) {
+    const int NP = nt16 * 16;
+    const size_t stage = (size_t)4 * kNBuf * (M + n_stage) * kTS, part = (size_t)4 * NP * 24;
+    return ((size_t)2 * NP * kK5S + NP + kTS + (stage > part ? stage : part)) * sizeof(float);
+}
+
 static bool plan_grad_mma(const Tables *t, int B, int I, int M, MmaGradPlan *pl) {
     if (M > 24 || M < 2 || I % kTC != 0 || t->n_max > 64 || t->p_out == 0) return false;
     pl->nt16 = (t->n_max + 15) / 16;
@@ -1358,23 +1366,26 @@ static bool plan_grad_mma(const Tables *t, int B, int I, int M, MmaGradPlan *pl)
     if (gy < 1) gy = 1;
     pl->tiles_per_cta = (int)(ceil_div(ceil_div(n_tiles, gy), 4) * 4);
     pl->gy = (int)ceil_div(n_tiles, pl->tiles_per_cta);
-    const int NP = pl->nt16 * 16;
-    size_t stage = (size_t)4 * kNBuf * (M + t->n_max) * kTS, part = (size_t)4 * NP * 24;
-    pl->smem = ((size_t)2 * NP * kK5S + NP + kTS + (stage > part ? stage : part)) * sizeof(float);
+    pl->smem = grad_mma_smem(pl->nt16, M, t->n_max);
     return true;
 }
 
+// One launch = the slots [slot0, slot0 + n_slots) of the processing order (vertices sorted by neighbour count,
+// descending), all of which have at most min(16 * NT16, n_stage) neighbours.
 template <int NT16, bool X3>
 static int launch_grad_mma(const Tables *t, const MmaGradPlan &pl, const float *dz, const float *x, const float *A,
-                           float *target, float *dG, int B, int I, int M, cudaStream_t st) {
-    dim3 grid((unsigned)t->p_out, (unsigned)pl.gy);
+                           float *target, float *dG, int B, int I, int M, cudaStream_t st, int slot0, int n_slots,
+                           int n_stage) {
+    if (n_slots <= 0) return VCM_OK;
+    dim3 grid((unsigned)n_slots, (unsigned)pl.gy);
     const int2 *meta = reinterpret_cast<const int2 *>(t->meta_sorted);
+    const size_t smem = grad_mma_smem(NT16, M, n_stage);
 #define VCM_K5M(DA_, DG_)                                                                                           \
     do {                                                                                                            \
         auto k = coeff_grad_mma_kernel<NT16, X3, DA_, DG_>;                                                         \
-        if (int e = set_smem(k, pl.smem)) return e;                                                                 \
-        k<<<grid, 128, pl.smem, st>>>(t->idx_sorted, meta, dz, x, A, target, dG, t->p_in, t->p_out, t->n_max, I, M, \
-                                      B, pl.tiles_per_cta);                                                         \
+        if (int e = set_smem(k, smem)) return e;                                                                    \
+        k<<<grid, 128, smem, st>>>(t->idx_sorted, meta, dz, x, A, target, dG, t->p_in, t->p_out, t->n_max, I, M,   \
+                                   B, pl.tiles_per_cta, slot0, n_stage);                                            \
     } while (0)
     if (target != nullptr && dG != nullptr) VCM_K5M(true, true);
     else if (target != nullptr) VCM_K5M(true, false);
@@ -1400,19 +1411,28 @@ size_t vcm_coeff_grad_workspace_ex(const vcm_tables *h, int B, int I, int M, int
     return need;
 }
 
+// Tensor-pipe K5 (shared-memory staged tiles, ldmatrix fragments): in TF32 mode it is the default for layers with
+// <= 32 neighbours per vertex, where it is 17-27 % faster than the fp32 kernel (C2 step: 3.49 -> 3.38 ms); with
+// more neighbours (the pooling layers) the coefficient fragments no longer fit in registers and the fp32 kernel
+// wins. VCM_K5_MMA: 0 = never, 1 = wherever it applies (also in tf32x3 mode), 2 = the default rule.
+static bool use_grad_mma(const vcm::Tables *t, int B, int I, int M, int precision, vcm::MmaGradPlan *pl) {
+    using namespace vcm;
+    static const int use_mma = [] { const char *e = getenv("VCM_K5_MMA"); return e ? atoi(e) : 2; }();
+    if (!use_mma || precision == VCM_PREC_FP32 || t == nullptr || B <= 0 || !plan_grad_mma(t, B, I, M, pl)) return false;
+    return !(use_mma >= 2 && (pl->nt16 > 2 || precision != VCM_PREC_TF32));
+}
+
+int vcm_coeff_grad_variant(const vcm_tables *h, int B, int I, int M, int precision) {
+    vcm::MmaGradPlan pl;
+    return use_grad_mma(vcm::as_tables(h), B, I, M, precision, &pl) ? 1 : 0;
+}
+
 int vcm_coeff_grad_ex(const vcm_tables *h, const float *dz, const float *x, const float *A, float *dA, float *dG,
                       float *ws, int B, int I, int M, int precision, void *stream) {
     using namespace vcm;
     const Tables *t = as_tables(h);
-    // Tensor-pipe K5 (shared-memory staged tiles, ldmatrix fragments): in TF32 mode it is the default for layers with
-    // <= 32 neighbours per vertex, where it is 17-27 % faster than the fp32 kernel (C2 step: 3.49 -> 3.38 ms); with
-    // more neighbours (the pooling layers) the coefficient fragments no longer fit in registers and the fp32 kernel
-    // wins. VCM_K5_MMA: 0 = never, 1 = wherever it applies (also in tf32x3 mode), 2 = the default rule.
-    static const int use_mma = [] { const char *e = getenv("VCM_K5_MMA"); return e ? atoi(e) : 2; }();
     MmaGradPlan pl;
-    if (!use_mma || precision == VCM_PREC_FP32 || t == nullptr || B <= 0 || !plan_grad_mma(t, B, I, M, &pl) ||
-        (use_mma >= 2 && (pl.nt16 > 2 || precision != VCM_PREC_TF32)))
-        return vcm_coeff_grad(h, dz, x, A, dA, dG, ws, B, I, M, stream);
+    if (!use_grad_mma(t, B, I, M, precision, &pl)) return vcm_coeff_grad(h, dz, x, A, dA, dG, ws, B, I, M, stream);
     VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR_OPT(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
     VCM_CHECK(dA != nullptr || dG != nullptr, "nothing to compute: dA and dG are both NULL");
     if (dA != nullptr && pl.gy > 1 && ws == nullptr) return fail(VCM_EINVAL, "workspace required (%d splits)", pl.gy);
@@ -1420,12 +1440,28 @@ int vcm_coeff_grad_ex(const vcm_tables *h, const float *dz, const float *x, cons
     cudaStream_t st = (cudaStream_t)stream;
     const bool x3 = precision == VCM_PREC_TF32X3;
     int e = VCM_OK;
+    // Degree buckets: the processing order lists the vertices by neighbour count, descending, so the vertices with
+    // more than 16 neighbours are the first n_gt16 slots. With 17..32 table columns they get the 32-neighbour kernel;
+    // everything behind them runs the 16-neighbour kernel with a 16-row staging area (4 instead of 3 CTAs per SM,
+    // half the fragment registers). Both launches write disjoint rows of dA / dG.
+#define VCM_K5L(NT_, S0_, NS_, ST_)                                                                          \
+    (x3 ? launch_grad_mma<NT_, true>(t, pl, dz, x, A, target, dG, B, I, M, st, S0_, NS_, ST_)                \
+        : launch_grad_mma<NT_, false>(t, pl, dz, x, A, target, dG, B, I, M, st, S0_, NS_, ST_))
+    static const int bucketed = [] { const char *e2 = getenv("VCM_K5_BUCKETS"); return e2 ? atoi(e2) : 1; }();
     switch (pl.nt16) {
-        case 1: e = x3 ? launch_grad_mma<1, true>(t, pl, dz, x, A, target, dG, B, I, M, st) : launch_grad_mma<1, false>(t, pl, dz, x, A, target, dG, B, I, M, st); break;
-        case 2: e = x3 ? launch_grad_mma<2, true>(t, pl, dz, x, A, target, dG, B, I, M, st) : launch_grad_mma<2, false>(t, pl, dz, x, A, target, dG, B, I, M, st); break;
-        case 3: e = x3 ? launch_grad_mma<3, true>(t, pl, dz, x, A, target, dG, B, I, M, st) : launch_grad_mma<3, false>(t, pl, dz, x, A, target, dG, B, I, M, st); break;
-        default: e = x3 ? launch_grad_mma<4, true>(t, pl, dz, x, A, target, dG, B, I, M, st) : launch_grad_mma<4, false>(t, pl, dz, x, A, target, dG, B, I, M, st); break;
+        case 1: e = VCM_K5L(1, 0, t->p_out, t->n_max); break;
+        case 2:
+            if (bucketed && t->n_gt16 < t->p_out) {
+                e = VCM_K5L(2, 0, t->n_gt16, t->n_max);
+                if (!e) e = VCM_K5L(1, t->n_gt16, t->p_out - t->n_gt16, 16);
+            } else {
+                e = VCM_K5L(2, 0, t->p_out, t->n_max);
+            }
+            break;
+        case 3: e = VCM_K5L(3, 0, t->p_out, t->n_max); break;
+        default: e = VCM_K5L(4, 0, t->p_out, t->n_max); break;
     }
+#undef VCM_K5L
     if (e) return e;
     if (dA != nullptr && pl.gy > 1) {
         const size_t n_dA = (size_t)t->p_out * t->n_max * M;

@@ -135,6 +135,8 @@ int vcm_tables_create(const int32_t *table, int p_out, int cols, int p_in, vcm_t
     t->n_max = n_max;
     t->max_last = max_last;
     t->max_rev = max_rev;
+    t->n_gt16 = 0;
+    for (int p = 0; p < p_out; ++p) t->n_gt16 += last[p] > 16;
     t->nnz = nnz;
     cudaGetDevice(&t->device);
 

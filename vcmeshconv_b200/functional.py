@@ -118,7 +118,10 @@ def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
     split = need_dx and direct_dA and _da_stream is not None
     ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws and not split else None
     st = _lib.stream_ptr()
-    nnz, tag = t.nnz, "P%d>%d I%d M%d" % (p_in, t.p_out, I, M)
+    nnz = t.nnz
+    # the tag names the layer shape and the kernel that serves it (bench.py groups timings by kernel)
+    tag = "P%d>%d I%d M%d %s" % (p_in, t.p_out, I, M, "mma" if L.vcm_coeff_grad_variant(t.handle, B, I, M, precision)
+                                 else "fp32")
     gb = 4 * B * nnz * I
     if split:
         # Only dG is on the backward chain (dG -> K6 -> dx -> next layer); dA goes straight into the flat gradient
