@@ -212,10 +212,16 @@ class MCEnc(nn.Module):
                                     structure.residual_rate)
         self.out_nrpts = structure.ptnum_list[self.layer_num]
         self.out_nrchs = channel_lst[self.layer_num]
+        # {layer index: tensor hook on that layer's input}: set by the trainer, which starts reducing / applying the
+        # gradients of the layers behind a point of the backward pass as soon as it has passed that point
+        self.activation_hooks = {}
 
     def forward_till_layer_n(self, in_pc, vcoeffs, layer_n):
         out_pc = in_pc
         for i in range(layer_n):
+            hook = self.activation_hooks.get(i)
+            if hook is not None and out_pc.requires_grad:
+                out_pc.register_hook(hook)       # fires when d loss / d (input of layer i) is complete
             out_pc = self.layer_lst[i](out_pc, vcoeffs.vcoeffs_list[i], is_final_layer=False,
                                        b_max_pool=self.b_max_pool)
         return out_pc
@@ -228,6 +234,9 @@ class MCEnc(nn.Module):
         h = self.forward_till_layer_n(in_pc, vcoeffs, last)
         if self.b_max_pool:
             raise NotImplementedError("b_max_pool is not supported")
+        hook = self.activation_hooks.get(last)
+        if hook is not None and h.requires_grad:
+            h.register_hook(hook)
         head = self.layer_lst[last]
         # mu and std heads share input, table and coefficients: one gather/contract, two basis GEMMs
         z = F_.gather_contract(h, vcoeffs.vcoeffs_list[last], head.tables(h.device))

@@ -148,7 +148,9 @@ class FlatBuffers:
     fp32 buffers. Layout follows backward order (decoder last layer first) so a
     bucket is a contiguous slice that becomes ready as a whole."""
 
-    def __init__(self, params, bucket_bytes=32 << 20):
+    def __init__(self, params, bucket_bytes=32 << 20, grad_alloc=None):
+        """`grad_alloc(n)` may supply the gradient buffer (e.g. a symmetric-memory allocation that peer GPUs can
+        address); default torch.zeros."""
         params = list(params)
         dev = params[0].device
         # autograd reaches parameters roughly in reverse creation order of use; bucket order only
@@ -162,7 +164,8 @@ class FlatBuffers:
             total += pad(n)
         self.total = total
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_g = grad_alloc(total).zero_() if grad_alloc is not None else torch.zeros(total, device=dev,
+                                                                                            dtype=torch.float32)
         self.offsets = offs
         for p, o in zip(params, offs):
             n = p.numel()
@@ -199,9 +202,21 @@ class DataParallelTrainer:
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         # flat layout: decoder side (layers, then coefficients) first, encoder side after it, so that "everything
         # whose gradient is final when the decoder's backward pass ends" is one contiguous range [0, early_split)
-        dec_side, enc_side = self._split_params(model)
-        self.flat = FlatBuffers(dec_side + enc_side, bucket_bytes)
-        self.early_split = (self.flat.offsets[len(dec_side)] if enc_side else self.flat.total) if dec_side else 0
+        # (the flat buffers are laid out in the order in which gradients become final: decoder side, then the late
+        # encoder layers and heads, then the first encoder layers, whose backward pass ends the step)
+        segs, self._enc_hook_layer = self._split_params(model)
+        ordered = [p for seg in segs for p in seg]
+        self._symm_op, grad_alloc = self._symmetric_allreduce(ordered)
+        self.flat = FlatBuffers(ordered, bucket_bytes, grad_alloc)
+        if self._symm_op is not None:
+            self._symm_mem.rendezvous(self.flat.flat_g, self._symm_group)
+        # early_bounds[i] = end of segment i in the flat buffers; the last segment is never "early"
+        ends, n = [], 0
+        for seg in segs:
+            n += len(seg)
+            ends.append(self.flat.offsets[n] if n < len(ordered) else self.flat.total)
+        self.early_bounds = ends[:-1]
+        self.early_split = self.early_bounds[0] if self.early_bounds else 0
         self.exp_avg = torch.zeros_like(self.flat.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat.flat_p)
         # optimizer scalars live on the device so a captured step can be replayed: {step, lr, 1-b1^t, sqrt(1-b2^t)}
@@ -225,6 +240,7 @@ class DataParallelTrainer:
         self.early_stream = (torch.cuda.Stream(self.flat.flat_p.device)
                              if self.flat.flat_p.is_cuda and os.environ.get("VCM_EARLY_UPDATE", "1") == "1" else None)
         self._advanced = self._early_done = False
+        self._early_upto = 0
         self.overlap = overlap and self.world > 1
         self._pending = []
         self._handles = []
@@ -234,13 +250,63 @@ class DataParallelTrainer:
         if self.world > 1:
             self.broadcast_parameters()
 
+    def _symmetric_allreduce(self, params):
+        """The flat gradient buffer of a multi-GPU job lives in a symmetric-memory allocation (every GPU of the node
+        maps every peer's buffer over NVLink; `multimem` additionally through the NVSwitch multicast object) and is
+        reduced by torch's symmetric-memory kernels (VCM_SYMM_AR=two_shot, the default | multimem | 0 = NCCL). They
+        are plain kernels with device-side barriers, so - unlike c10d's NCCL calls, whose capture hung here - they
+        are captured inside the step graph: the gradient segments are reduced on the early branch next to the rest
+        of the backward pass and the whole multi-GPU step is ONE graph launch (8 x B200: 2.62 vs 2.80 ms/step with
+        NCCL between two graphs). Returns (op name or None, allocator or None); falls back to NCCL when the
+        allocation is not available."""
+        mode = os.environ.get("VCM_SYMM_AR", "two_shot")
+        if mode in ("0", "") or self.world == 1 or not params or not params[0].is_cuda:
+            return None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            op = {"two_shot": "two_shot_all_reduce_", "multimem": "multimem_all_reduce_"}[mode]
+            getattr(torch.ops.symm_mem, op)
+            self._symm_mem = symm_mem
+            self._symm_group = (self.group if self.group is not None else dist.group.WORLD).group_name
+            dev = params[0].device
+            symm_mem.rendezvous(symm_mem.empty(64, dtype=torch.float32, device=dev), self._symm_group)   # probe
+            return op, (lambda n: symm_mem.empty(n, dtype=torch.float32, device=dev))
+        except Exception as e:                   # no symmetric memory on this system: NCCL between two graphs
+            import sys
+            sys.stderr.write("vcmeshconv_b200: symmetric-memory all-reduce unavailable (%r), using NCCL\n" % (e,))
+            return None, None
+
+    def _allreduce(self, lo, hi):
+        """SUM over ranks of flat_g[lo:hi], in place, on the current stream."""
+        if hi <= lo:
+            return
+        if self._symm_op is not None:
+            getattr(torch.ops.symm_mem, self._symm_op)(self.flat.flat_g[lo:hi], "sum", self._symm_group)
+        else:
+            dist.all_reduce(self.flat.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
     @staticmethod
     def _split_params(model):
+        """Trainable parameters as segments in the order in which their gradients become final during the backward
+        pass: [decoder layers + decoder coefficients], [encoder layers >= k, both heads, their coefficients],
+        [encoder layers < k and their coefficients]. Returns (segments, k); models without that structure are one
+        segment."""
         params = model.trainable_parameters()
-        if not (hasattr(model, "net_geodec") and hasattr(model, "mcvcoeffsdec")):
-            return [], params
-        dec_ids = {id(p) for p in model.net_geodec.parameters()} | {id(p) for p in model.mcvcoeffsdec.parameters()}
-        return [p for p in params if id(p) in dec_ids], [p for p in params if id(p) not in dec_ids]
+        need = ("net_geodec", "mcvcoeffsdec", "net_geoenc", "mcvcoeffsenc")
+        if not all(hasattr(model, a) for a in need):
+            return [params], None
+        enc = model.net_geoenc
+        k = min(2, enc.layer_num - 1)
+        ident = lambda ps: {id(p) for p in ps}
+        dec_ids = ident(model.net_geodec.parameters()) | ident(model.mcvcoeffsdec.parameters())
+        late_ids = ident(enc.stdlayer.parameters())
+        for i in range(k, enc.layer_num):
+            late_ids |= ident(enc.layer_lst[i].parameters()) | {id(model.mcvcoeffsenc.vcoeffs_list[i])}
+        segs = [[p for p in params if id(p) in dec_ids],
+                [p for p in params if id(p) in late_ids and id(p) not in dec_ids],
+                [p for p in params if id(p) not in dec_ids and id(p) not in late_ids]]
+        segs = [seg for seg in segs if seg]
+        return segs, (k if len(segs) == 3 else None)
 
     # -- communication ------------------------------------------------------------
     def broadcast_parameters(self):
@@ -282,9 +348,7 @@ class DataParallelTrainer:
                 h.wait()
             self._handles = []
         else:
-            lo = self.early_split if self._early_done else 0           # [0, lo) was reduced next to the backward pass
-            if lo < self.flat.total:
-                dist.all_reduce(self.flat.flat_g[lo:], op=dist.ReduceOp.SUM, group=self.group)
+            self._allreduce(self._early_upto, self.flat.total)      # [0, _early_upto) was reduced next to the backward pass
 
     # -- one training step ---------------------------------------------------------
     def _set_direct_grads(self, on):
@@ -302,10 +366,13 @@ class DataParallelTrainer:
         F_.begin_step(self.flat.params)
         self._early_done = False
         cur = torch.cuda.current_stream() if self.flat.flat_p.is_cuda else None
-        if early and self.early_stream is not None and self.early_split > 0 and not self.overlap:
+        self._early_upto = 0
+        if early and self.early_stream is not None and self.early_bounds and not self.overlap:
             self._advance()                              # this step's optimizer scalars, before anything applies them
             self.early_stream.wait_stream(cur)
-            self.model.latent_grad_hook = self._decoder_backward_done
+            self.model.latent_grad_hook = lambda grad: self._segment_done(0)
+            if self._enc_hook_layer is not None:
+                self.model.net_geoenc.activation_hooks = {self._enc_hook_layer: lambda grad: self._segment_done(1)}
         if self.res_stream is not None and not self.overlap:
             F_.set_residual_stream(self.res_stream)
         if self.prep_stream is not None:
@@ -329,12 +396,16 @@ class DataParallelTrainer:
             F_.set_da_stream(None)
             if getattr(self.model, "latent_grad_hook", None) is not None:
                 self.model.latent_grad_hook = None
+                self.model.net_geoenc.activation_hooks = {}
                 cur.wait_stream(self.early_stream)
         return loss.detach(), (l1.detach(), lap.detach(), kl.detach(), lnor.detach())
 
-    def _decoder_backward_done(self, grad):
-        """Tensor hook on the latent code: autograd runs nodes in reverse creation order, so when d loss / d latent
-        is complete every decoder-side backward kernel has been enqueued (on the chain or on a branch stream)."""
+    def _segment_done(self, i):
+        """Tensor hook (on the latent code for segment 0, on the input of encoder layer k for segment 1): autograd
+        runs nodes in reverse creation order, so when the gradient of that activation is complete every backward
+        kernel of the layers behind it has been enqueued (on the chain or on a branch stream) and the gradients of
+        segment i are final: reduce them over the ranks and apply Adam on the early stream."""
+        lo, hi = self._early_upto, self.early_bounds[i]
         s = self.early_stream
         s.wait_stream(torch.cuda.current_stream())
         for st in (F_._side_stream, F_._da_stream, self.res_stream):
@@ -342,8 +413,9 @@ class DataParallelTrainer:
                 s.wait_stream(st)
         with torch.cuda.stream(s):
             if self.world > 1:
-                dist.all_reduce(self.flat.flat_g[:self.early_split], op=dist.ReduceOp.SUM, group=self.group)
-            self._apply(0, self.early_split)
+                self._allreduce(lo, hi)
+            self._apply(lo, hi)
+        self._early_upto = hi
         self._early_done = True
 
     @property
@@ -374,8 +446,9 @@ class DataParallelTrainer:
             raise RuntimeError("the optimizer step runs on CUDA only (no CPU fallback)")
         if not self._advanced:
             self._advance()
-        self._apply(self.early_split if self._early_done else 0, f.total)
+        self._apply(self._early_upto, f.total)
         self._advanced = self._early_done = False
+        self._early_upto = 0
 
     def step(self, pc, nor, eps=None):
         if self._graph is not None and eps is None:
@@ -442,7 +515,8 @@ class DataParallelTrainer:
             for _ in range(warmup):
                 if self.static_eps is not None:
                     self.static_eps.normal_()
-                self.forward_backward(self.static_pc, self.static_nor, self.static_eps, early=self.world == 1)
+                self.forward_backward(self.static_pc, self.static_nor, self.static_eps,
+                                      early=self.world == 1 or self._symm_op is not None)
                 self._finish_reduction()
                 self.optimizer_step()
         torch.cuda.current_stream().wait_stream(side)
@@ -452,7 +526,7 @@ class DataParallelTrainer:
         # gradient buffer -> graph(Adam). VCM_GRAPH_NCCL=1 captures the all-reduces as well (decoder-side range on
         # the early stream, the rest after the backward pass; one graph per step) -- opt-in: with c10d's NCCL
         # process group that capture hung on 2 x B200 in this image (torch 2.11 / NCCL 2.28), so it is not the default.
-        nccl_in_graph = self.world == 1 or os.environ.get("VCM_GRAPH_NCCL", "0") == "1"
+        nccl_in_graph = self.world == 1 or os.environ.get("VCM_GRAPH_NCCL", "0") == "1" or self._symm_op is not None
         g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_fb, capture_error_mode="relaxed"):
             self.static_loss, self.static_parts = self.forward_backward(self.static_pc, self.static_nor,
