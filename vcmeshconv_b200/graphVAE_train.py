@@ -207,9 +207,17 @@ class DataParallelTrainer:
         segs, self._enc_hook_layer = self._split_params(model)
         ordered = [p for seg in segs for p in seg]
         self._symm_op, grad_alloc = self._symmetric_allreduce(ordered)
-        self.flat = FlatBuffers(ordered, bucket_bytes, grad_alloc)
-        if self._symm_op is not None:
-            self._symm_mem.rendezvous(self.flat.flat_g, self._symm_group)
+        try:
+            self.flat = FlatBuffers(ordered, bucket_bytes, grad_alloc)
+            if self._symm_op is not None:
+                self._symm_mem.rendezvous(self.flat.flat_g, self._symm_group)
+        except Exception as e:                   # no symmetric memory on this system: NCCL between two graphs
+            if grad_alloc is None:
+                raise
+            import sys
+            sys.stderr.write("vcmeshconv_b200: symmetric-memory all-reduce unavailable (%r), using NCCL\n" % (e,))
+            self._symm_op = None
+            self.flat = FlatBuffers(ordered, bucket_bytes)
         # early_bounds[i] = end of segment i in the flat buffers; the last segment is never "early"
         ends, n = [], 0
         for seg in segs:
@@ -257,24 +265,17 @@ class DataParallelTrainer:
         are plain kernels with device-side barriers, so - unlike c10d's NCCL calls, whose capture hung here - they
         are captured inside the step graph: the gradient segments are reduced on the early branch next to the rest
         of the backward pass and the whole multi-GPU step is ONE graph launch (8 x B200: 2.62 vs 2.80 ms/step with
-        NCCL between two graphs). Returns (op name or None, allocator or None); falls back to NCCL when the
-        allocation is not available."""
+        NCCL between two graphs). Returns (op name or None, allocator or None); the caller falls back to NCCL when
+        the allocation is not available."""
         mode = os.environ.get("VCM_SYMM_AR", "two_shot")
         if mode in ("0", "") or self.world == 1 or not params or not params[0].is_cuda:
             return None, None
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-            op = {"two_shot": "two_shot_all_reduce_", "multimem": "multimem_all_reduce_"}[mode]
-            getattr(torch.ops.symm_mem, op)
-            self._symm_mem = symm_mem
-            self._symm_group = (self.group if self.group is not None else dist.group.WORLD).group_name
-            dev = params[0].device
-            symm_mem.rendezvous(symm_mem.empty(64, dtype=torch.float32, device=dev), self._symm_group)   # probe
-            return op, (lambda n: symm_mem.empty(n, dtype=torch.float32, device=dev))
-        except Exception as e:                   # no symmetric memory on this system: NCCL between two graphs
-            import sys
-            sys.stderr.write("vcmeshconv_b200: symmetric-memory all-reduce unavailable (%r), using NCCL\n" % (e,))
-            return None, None
+        import torch.distributed._symmetric_memory as symm_mem
+        op = {"two_shot": "two_shot_all_reduce_", "multimem": "multimem_all_reduce_"}[mode]
+        self._symm_mem = symm_mem
+        self._symm_group = (self.group if self.group is not None else dist.group.WORLD).group_name
+        dev = params[0].device
+        return op, (lambda n: symm_mem.empty(n, dtype=torch.float32, device=dev))
 
     def _allreduce(self, lo, hi):
         """SUM over ranks of flat_g[lo:hi], in place, on the current stream."""
