@@ -49,17 +49,20 @@ def _worker(rank, world, port, overlap, out):
             with torch.no_grad():
                 for p in model.parameters():
                     p.add_(1.0)
-        tr = DataParallelTrainer(model, bucket_bytes=256, overlap=overlap)
+        tr = DataParallelTrainer(model, bucket_bytes=256, overlap=overlap is True)
         torch.manual_seed(100 + rank)
         x = torch.randn(8, 37)
         tr.forward_backward(x, None)
+        if overlap == "split":                            # a range already reduced "early": only the rest is left
+            tr._allreduce(0, 64)
+            tr._early_upto = 64
         tr._finish_reduction()
         out[rank] = (tr.flat.flat_g.clone(), tr.flat.flat_p.clone(), x)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [True, False])
+@pytest.mark.parametrize("overlap", [True, False, "split"])
 def test_sum_allreduce_matches_single_process(overlap):
     world = 2
     with mp.Manager() as mgr:

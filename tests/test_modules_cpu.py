@@ -80,3 +80,43 @@ def test_stack_containers():
             assert tuple(sd[k].shape) == v.shape, (tag, k)
         mod.load_state_dict({k: torch.from_numpy(v).to(sd[k].dtype) for k, v in want.items()})
     assert s_enc.ptnum_list[0] == 300 and enc.out_nrchs == int(g["enc_channels"][-1])
+
+
+def test_trainer_segments_follow_gradient_completion_order():
+    """DataParallelTrainer lays the flat buffers out in the order in which gradients become final during the
+    backward pass (decoder side | late encoder layers + heads | first encoder layers): every trainable parameter
+    in exactly one segment, relative order inside a segment unchanged, and the hooked encoder layer index valid."""
+    from vcmeshconv_b200 import graph_sampling, synthetic
+    from vcmeshconv_b200 import graphVAE_train as T
+    pts, faces = synthetic.sphere(600, seed=0)
+    tabs, _ = graph_sampling.build_tables(faces, 600, synthetic.alternating_levels(5))
+    enc = [tabs["pool%d" % l] for l in range(1, 4)]
+    dec = [tabs["unpool%d" % l] for l in range(3, 0, -1)]
+    model = T.Net_autoenc(T.make_param(enc, dec, tabs["pool0"], 600, 0.9), faces, enc_channels=[3, 16, 32, 8],
+                          dec_channels=[8, 32, 16, 3], weight_num=9)
+    params = model.trainable_parameters()
+    segs, k = T.DataParallelTrainer._split_params(model)
+    assert len(segs) == 3 and k == 2
+    flat = [p for s in segs for p in s]
+    assert sorted(map(id, flat)) == sorted(map(id, params)) and len(set(map(id, flat))) == len(params)
+    order = {id(p): i for i, p in enumerate(params)}
+    for s in segs:
+        assert [order[id(p)] for p in s] == sorted(order[id(p)] for p in s)
+    dec_ids = {id(p) for p in model.net_geodec.parameters()} | {id(p) for p in model.mcvcoeffsdec.parameters()}
+    assert {id(p) for p in segs[0]} == dec_ids
+    enc_m = model.net_geoenc
+    tail = {id(p) for i in range(k) for p in enc_m.layer_lst[i].parameters()} | \
+           {id(model.mcvcoeffsenc.vcoeffs_list[i]) for i in range(k)}
+    assert {id(p) for p in segs[2]} == tail
+    late = {id(p) for p in segs[1]}
+    assert {id(p) for p in enc_m.stdlayer.parameters()} <= late and id(model.mcvcoeffsenc.vcoeffs_list[k]) in late
+    # a model without the autoencoder structure is one segment
+    class Plain(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(3))
+
+        def trainable_parameters(self):
+            return [self.w]
+    segs1, k1 = T.DataParallelTrainer._split_params(Plain())
+    assert len(segs1) == 1 and k1 is None
