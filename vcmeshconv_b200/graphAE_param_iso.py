@@ -6,7 +6,8 @@ Differences, all deliberate: no side effects besides creating the two output
 folders (the reference also opens a tensorboardX writer here, :33-34); a layer
 name that matches no file in `connection_folder` raises instead of printing
 "!!!ERROR" and continuing (:112-113); data-set keys that are absent are simply
-left unset (this package trains on tensors, PLY I/O is out of scope).
+left unset (vcmeshconv_b200/train.py needs template_ply_fn, mesh_train and
+frame_list; tensors can be fed to the trainer directly without them).
 """
 import configparser
 import json
