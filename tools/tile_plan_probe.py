@@ -6,6 +6,7 @@ report tile fill and K. In table / processing order consecutive vertices share a
 7 x the per-vertex count), so the kernel needs such a spatial tile plan next to the degree-sorted order.
 
     python tools/tile_plan_probe.py [T] [KMAX]
+    python tools/tile_plan_probe.py check        numerical check of the dense-tile formulation on one layer
 """
 import collections
 import os
@@ -15,6 +16,44 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
 import bench
+
+
+plan = []          # [(output vertices of the tile, sorted distinct neighbour ids)] of the last greedy() call
+
+
+def check(T=7, KMAX=64, M=17, I=8, B=3):
+    """z[b,p,m,i] = sum_n A[p,n,m] x[b,idx[p,n],i] computed tile by tile as ONE dense product per tile,
+    z_tile[(p,m), (b,i)] = S_tile[(p,m), k] @ X_tile[k, (b,i)] with S_tile the zero-padded local coefficient matrix
+    (k = position of a neighbour in the tile's distinct-neighbour list), against the direct sum."""
+    pts, faces, tabs, nums = bench.build_tables(6890)
+    table = tabs["unpool2"]                                   # 1811 -> 1811 convolution layer
+    greedy(table, nums, T, KMAX)
+    P, ids = table.shape[0], table[:, 1::2]
+    mx = int(ids.max())
+    p_in = mx if mx in nums else mx + 1
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((P, ids.shape[1], M))
+    x = rng.standard_normal((B, p_in, I))
+    xpad = np.concatenate([x, np.zeros((B, 1, I))], 1)
+    mask = (ids != p_in)[:, :, None]
+    want = np.einsum("pnm,bpni->bpmi", A * mask, xpad[:, ids])               # graphVAESSW.py:111-123
+    got = np.zeros_like(want)
+    for verts, nbrs in plan:
+        K = (len(nbrs) + 7) // 8 * 8                                          # MMA k granularity
+        col = {q: k for k, q in enumerate(nbrs)}
+        S = np.zeros((len(verts) * M, K))
+        for r, p in enumerate(verts):
+            for n in range(ids.shape[1]):
+                q = int(ids[p, n])
+                if q != p_in:
+                    S[r * M:(r + 1) * M, col[q]] += A[p, n]
+        X = np.zeros((K, B * I))
+        X[:len(nbrs)] = x[:, nbrs].transpose(1, 0, 2).reshape(len(nbrs), B * I)
+        Z = S @ X                                                             # [(p,m), (b,i)]
+        got[:, verts] = Z.reshape(len(verts), M, B, I).transpose(2, 0, 1, 3)
+    err = np.abs(got - want).max() / np.abs(want).max()
+    print("dense-tile formulation vs direct sum on unpool2 (%d tiles): max rel err %.2e" % (len(plan), err))
+    assert err < 1e-12
 
 
 def greedy(table, nums, T, KMAX):
@@ -27,6 +66,7 @@ def greedy(table, nums, T, KMAX):
         for q in nb[p]:
             rev[q].append(p)
     done, tiles = np.zeros(P, bool), []
+    plan.clear()
     for p0 in range(P):
         if done[p0]:
             continue
@@ -47,10 +87,13 @@ def greedy(table, nums, T, KMAX):
             done[best] = True
             u.update(nb[best])
         tiles.append((len(tile), len(u)))
+        plan.append((tile, sorted(u)))
     return np.array(tiles), float(np.mean([len(x) for x in nb]))
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "check":
+        return check()
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 7
     KMAX = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     pts, faces, tabs, nums = bench.build_tables(6890)
