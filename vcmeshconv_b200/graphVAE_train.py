@@ -8,15 +8,20 @@ is on the hot path (e):
                         signature and 5-tuple of [1]-shaped losses
   DataParallelTrainer   replaces nn.DataParallel (:277) + Adam (:252-262, :316):
                         one process per GPU, parameters resident on every GPU,
-                        gradients produced directly inside ONE flat fp32 buffer
-                        that NCCL all-reduces in place (SUM — the reference sums
-                        per-replica mean losses, :249/:315), bucketed in reverse
-                        layer order and launched from autograd hooks so the
-                        reduction hides under the rest of backward; then one
-                        fused Adam launch over the flat buffers on every rank.
+                        gradients produced directly inside ONE flat fp32 buffer,
+                        laid out in the order in which they become final during
+                        the backward pass and summed over the ranks (SUM - the
+                        reference sums per-replica mean losses, :249/:315)
+                        segment by segment while the backward pass is still
+                        running: in graph mode by symmetric-memory all-reduce
+                        kernels over NVLink peer memory captured in the step
+                        graph, eagerly by bucketed NCCL all-reduces launched from
+                        autograd hooks; a fused Adam launch per segment on every
+                        rank. The whole step replays as one CUDA graph.
 
-Data IO (PLY), tensorboard and the INI reader are out of scope;
-`Parameters` below only carries the fields the model needs.
+The INI reader is graphAE_param_iso.py, the PLY data path ply_dataset.py, the
+entry point train.py; tensorboard is out of scope. `make_param`
+below builds the fields the model needs from in-memory tables.
 """
 import os
 import types
