@@ -185,6 +185,84 @@ def stack_case(name, tabs, n_vert, faces, seed):
           (name, rec["loss"], rec["loss_l1"], rec["loss_laplace"], rec["loss_kl"], rec["loss_normal"]))
 
 
+def checkpoint_case(name, tabs, n_vert, faces, seed):
+    """A checkpoint written the way the reference's trainer writes it (graphVAE_train.py:339-347: four module
+    state dicts + `optimizer.state_dict()` of the Adam built by getoptim, :252-262) after two fp32 training steps
+    of the reference's own modules, plus the inputs of a third step and the parameters the reference holds after
+    it. tests/ load the file into DataParallelTrainer, take the third step on the GPU and must land on the same
+    parameters (which only happens if moments, step count and learning rate were all taken over)."""
+    import itertools
+    m = 5
+    enc_names, dec_names = ["pool1", "pool2", "pool3"], ["unpool3", "unpool2", "unpool1"]
+    enc_ch, dec_ch = [3, 8, 16, 4], [4, 16, 8, 3]
+    resid, lr = 0.9, 2e-3
+    gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    with tempfile.TemporaryDirectory() as d:
+        paths = {}
+        for k, v in tabs.items():
+            paths[k] = os.path.join(d, "_%s.npy" % k)
+            np.save(paths[k], v)
+        param = types.SimpleNamespace(residual_rate=resid, conv_max=0,
+                                      connection_layer_fn_lst_enc=[paths[k] for k in enc_names],
+                                      connection_layer_fn_lst_dec=[paths[k] for k in dec_names])
+        t0 = tabs["pool0"]
+        param.neighbor_id_lstlst = t0[:, 1:].reshape(t0.shape[0], -1, 2)[:, :, 0]
+        param.neighbor_num_lst = t0[:, 0]
+        s_enc = quiet(ref.MCStructure, param, n_vert, m, bDec=False)
+        vc_enc = quiet(ref.MCVcoeffs, s_enc, m)
+        enc = quiet(ref.MCEnc, s_enc, enc_ch, m)
+        s_dec = quiet(ref.MCStructure, param, enc.out_nrpts, m, bDec=True)
+        vc_dec = quiet(ref.MCVcoeffs, s_dec, m)
+        dec = quiet(ref.MCDec, s_dec, dec_ch, m)
+        loss_mod = ref.MCLoss(param)
+    for mod in (enc, dec):
+        randomise(mod, gen)
+    # getoptim, graphVAE_train.py:252-262
+    params = [p for p in itertools.chain(dec.parameters(), enc.parameters(), vc_dec.parameters(), vc_enc.parameters())
+              if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999))
+    batch = 4
+    pts, _ = synthetic.sphere(n_vert, seed=seed)
+    f = torch.from_numpy(faces).long()
+    rec = {"n_vert": np.int64(n_vert), "weight_num": np.int64(m), "residual_rate": np.float64(resid), "lr": np.float64(lr),
+           "enc_channels": np.array(enc_ch), "dec_channels": np.array(dec_ch),
+           "enc_names": np.array(enc_names), "dec_names": np.array(dec_names), "faces": faces.astype(np.int32)}
+    for k, v in tabs.items():
+        rec["table." + k] = v.astype(np.int32)
+
+    def step(i):
+        x = (torch.from_numpy(pts)[None] * 0.3 + torch.randn(batch, n_vert, 3, generator=gen) * 0.05).float()
+        nor = torch.from_numpy(synthetic.face_normals(x.numpy(), faces)).float()
+        eps = torch.randn(batch, enc.out_nrpts, enc_ch[-1], generator=gen)
+        mu, logstd = enc(x, vc_enc)                                                   # graphVAE_train.py:199-225
+        z = mu + logstd.exp() * eps
+        kl = torch.mean(-0.5 - logstd + 0.5 * mu ** 2 + 0.5 * torch.exp(2 * logstd))
+        out = dec(z, vc_dec)[:, :, 0:3]
+        dif = out - x
+        v0, v1, v2 = (ref.index_selection_nd(dif, f[:, c], 1) for c in range(3))
+        l_nor = ((v1 + v0 + v2) / 3.0 * nor).sum(2).pow(2).mean()
+        loss = (loss_mod.compute_geometric_loss_l1(x, out) * 1.0 + loss_mod.compute_laplace_loss_l2(x, out) * 100.0 +
+                kl * 1e-5 + l_nor * 10.0)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        rec["x%d" % i], rec["normals%d" % i], rec["eps%d" % i], rec["loss%d" % i] = x.numpy(), nor.numpy(), eps.numpy(), loss.item()
+
+    step(0)
+    step(1)
+    torch.save({"encgeo_state_dict": enc.state_dict(), "decgeo_state_dict": dec.state_dict(),
+                "mcvcoeffsdec_dict": vc_dec.state_dict(), "mcvcoeffsenc_dict": vc_enc.state_dict(),
+                "optimizer_state_dict": opt.state_dict()}, os.path.join(OUT, name + ".weight"))
+    step(2)
+    for tag, mod in (("enc", enc), ("dec", dec), ("vce", vc_enc), ("vcd", vc_dec)):
+        for k, v in mod.state_dict().items():
+            rec["after3.%s.%s" % (tag, k)] = v.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print("%-28s reference-made checkpoint after 2 Adam steps; losses %.5f %.5f %.5f" %
+          (name, rec["loss0"], rec["loss1"], rec["loss2"]))
+
+
 def main():
     if not graphsampling_ref.build():
         raise SystemExit("reference GraphSampling could not be built")
@@ -198,6 +276,8 @@ def main():
     layer_case("layer_conv_res_proj", tabs["pool2"], n[2], 8, 24, 17, 2, 0.9, True, False, 12)
     layer_case("layer_pool_res", tabs["pool1"], n[1], 12, 20, 17, 3, 0.9, True, False, 13)
     layer_case("layer_pool_plain", tabs["pool3"], n[3], 32, 64, 17, 2, 0.0, False, False, 14)
+    # shapes the tcgen05 GEMMs and the tensor-pipe K5 take (I, O multiples of 32, <= 32 neighbours)
+    layer_case("layer_conv_tc_res", tabs["pool2"], n[2], 32, 64, 17, 4, 0.9, True, False, 21)
     layer_case("layer_unpool_res_same", tabs["unpool1"], n[2], 16, 16, 7, 2, 0.9, True, False, 15)
     layer_case("layer_unpool_final", tabs["unpool3"], n[4], 32, 3, 17, 5, 0.9, True, True, 16)
     layer_case("layer_unpool_sharedbias", tabs["unpool1"], n[2], 6, 10, 3, 1, 0.0, False, True, 17)
@@ -207,6 +287,7 @@ def main():
     layer_case("layer_tets_conv", ttabs["pool0"], 160, 8, 16, 17, 2, 0.0, True, False, 18)
     layer_case("layer_tets_pool_res", ttabs["pool1"], 160, 8, 16, 17, 2, 0.9, True, False, 19)
     stack_case("stack_sphere300", tabs, 300, faces, 20)
+    checkpoint_case("ref_checkpoint_sphere300", tabs, 300, faces, 22)
 
 
 if __name__ == "__main__":

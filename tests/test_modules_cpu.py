@@ -38,7 +38,7 @@ def test_state_dict_layout_matches_reference(case):
 
 SEEDS = {"layer_conv_3to32": 10, "layer_conv_res_same": 11, "layer_conv_res_proj": 12, "layer_pool_res": 13,
          "layer_pool_plain": 14, "layer_unpool_res_same": 15, "layer_unpool_final": 16,
-         "layer_unpool_sharedbias": 17, "layer_tets_conv": 18, "layer_tets_pool_res": 19}
+         "layer_unpool_sharedbias": 17, "layer_tets_conv": 18, "layer_tets_pool_res": 19, "layer_conv_tc_res": 21}
 
 
 @pytest.mark.parametrize("case", layer_cases())

@@ -43,6 +43,10 @@ def _req(t, name):
         raise RuntimeError("%s must be a CUDA tensor: vcmeshconv_b200 has no CPU path" % name)
     if t.dtype != torch.float32:
         raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the current device's stream and the tables live on the tensor's device
+        raise RuntimeError("%s is on cuda:%d but the current device is cuda:%d (wrap the call in "
+                           "torch.cuda.device(...))" % (name, t.device.index, torch.cuda.current_device()))
     return t.contiguous()
 
 
@@ -55,7 +59,7 @@ def _grad_target(t):
     is a whole, order-preserving view of), if this is the first gradient written to it this step. The
     backward kernels then write there directly and autograd sees no gradient for the input: no temporary,
     no accumulate kernel, and the buffer NCCL reduces / Adam reads is filled in place."""
-    if t is None:
+    if t is None or not torch.is_grad_enabled():
         return None
     base = t._base if t._base is not None else t
     buf = getattr(base, "_vcm_grad_buf", None)

@@ -259,7 +259,7 @@ class DataParallelTrainer:
         self._handles = []
         if self.overlap:
             self._install_hooks()
-        self._set_direct_grads(not self.overlap)
+        self._direct = not self.overlap              # see forward_backward
         if self.world > 1:
             self.broadcast_parameters()
 
@@ -369,6 +369,9 @@ class DataParallelTrainer:
         backward pass is complete, next to the encoder's backward pass; the caller finishes the step with
         _finish_reduction() + optimizer_step(), which then only touch the rest."""
         self.flat.zero_grad()
+        # direct gradient writes (backward kernels fill the flat buffer in place, OVERWRITING it) are enabled for the
+        # duration of this call only: a backward() the user runs outside goes through ordinary autograd accumulation
+        self._set_direct_grads(self._direct)
         F_.begin_step(self.flat.params)
         self._early_done = False
         cur = torch.cuda.current_stream() if self.flat.flat_p.is_cuda else None
@@ -400,6 +403,9 @@ class DataParallelTrainer:
             F_.join_side_stream()
             F_.set_side_stream(None)
             F_.set_da_stream(None)
+            if self.res_stream is not None and cur is not None:
+                cur.wait_stream(self.res_stream)     # residual-branch backward kernels (p_neighbors / weight_res grads)
+            self._set_direct_grads(False)
             if getattr(self.model, "latent_grad_hook", None) is not None:
                 self.model.latent_grad_hook = None
                 self.model.net_geoenc.activation_hooks = {}
@@ -457,8 +463,8 @@ class DataParallelTrainer:
         self._early_upto = 0
 
     def step(self, pc, nor, eps=None):
-        if self._graph is not None and eps is None:
-            return self._graph_step(pc, nor)
+        if self._graph is not None and (eps is None or self.static_eps is not None):
+            return self._graph_step(pc, nor, eps)
         loss, parts = self.forward_backward(pc, nor, eps, early=True)
         self._finish_reduction()
         self.optimizer_step()
@@ -506,7 +512,7 @@ class DataParallelTrainer:
         dW GEMMs, the stacked-bases preparation and the early decoder-side Adam."""
         assert pc.is_cuda and self._graph is None
         self.overlap = False                         # no NCCL launches inside the capture
-        self._set_direct_grads(True)
+        self._direct = True
         self.static_pc, self.static_nor = pc.clone(), nor.clone()
         # the N(0,1) draw of the reparameterisation (graphVAE_train.py:201) stays outside the graph: one normal_()
         # launch in front of every replay, from torch's generator, instead of a captured generator (whose replay
@@ -515,6 +521,13 @@ class DataParallelTrainer:
         if os.environ.get("VCM_EPS_OUTSIDE", "1") == "1":
             m = self.model
             self.static_eps = torch.empty(pc.shape[0], m.nrpt_latent, m.net_geoenc.out_nrchs, device=pc.device)
+        # Capture needs a warmed-up process (library loaded, device tables created, kernel attributes set, every
+        # kernel's module resident). warmup=0 means "do not advance training": one warm-up step still runs, on a
+        # side stream, and parameters, moments and optimizer scalars are restored afterwards.
+        snapshot = None
+        if warmup <= 0:
+            snapshot = [t.clone() for t in (self.flat.flat_p, self.exp_avg, self.exp_avg_sq, self.opt_state)]
+            warmup = 1
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -526,6 +539,10 @@ class DataParallelTrainer:
                 self._finish_reduction()
                 self.optimizer_step()
         torch.cuda.current_stream().wait_stream(side)
+        if snapshot is not None:
+            with torch.no_grad():
+                for t, v in zip((self.flat.flat_p, self.exp_avg, self.exp_avg_sq, self.opt_state), snapshot):
+                    t.copy_(v)
         torch.cuda.synchronize()
         l0 = _lib.lib().vcm_launch_count()
         # world_size 1: one graph for the whole step. world_size > 1: graph(fwd + bwd) -> NCCL all-reduce of the flat
@@ -549,14 +566,19 @@ class DataParallelTrainer:
         self.graph_launches = int(_lib.lib().vcm_launch_count() - l0)     # our kernels inside one replayed step
         return self
 
-    def _graph_step(self, pc, nor):
+    def _graph_step(self, pc, nor, eps=None):
+        """One replay of the captured step. `eps` fixes the N(0,1) draw of the reparameterisation (tests and the
+        multi-GPU equivalence check compare runs on the same sample); default: a fresh draw from torch's generator."""
         if pc.data_ptr() != self.static_pc.data_ptr():
             self.static_pc.copy_(pc, non_blocking=True)
         if nor.data_ptr() != self.static_nor.data_ptr():
             self.static_nor.copy_(nor, non_blocking=True)
         g_fb, g_opt = self._graph
         if self.static_eps is not None:
-            self.static_eps.normal_()
+            if eps is not None:
+                self.static_eps.copy_(eps, non_blocking=True)
+            else:
+                self.static_eps.normal_()
         g_fb.replay()
         if g_opt is not None:
             dist.all_reduce(self.flat.flat_g, op=dist.ReduceOp.SUM, group=self.group)
@@ -564,32 +586,87 @@ class DataParallelTrainer:
         return self.static_loss, self.static_parts
 
     # -- checkpoint layout of the reference (graphVAE_train.py:339-347) ----------
+    def optimizer_state_dict(self):
+        """The Adam state exactly as `torch.optim.Adam.state_dict()` lays it out for the reference's optimizer
+        (graphVAE_train.py:252-262, 280, 345): `state[i]` = {step, exp_avg, exp_avg_sq} of the i-th parameter in
+        getoptim order (decoder, encoder, decoder coefficients, encoder coefficients), one param group. The flat
+        moment buffers are sliced per parameter, so the reference's `optimizer.load_state_dict(...)` (:291) accepts
+        the file and resumes with the right bias correction."""
+        step = float(self.step_count)
+        by_id = {id(p): (o, p) for p, o in zip(self.flat.params, self.flat.offsets)}
+        state, order = {}, self.model.trainable_parameters()
+        for i, p in enumerate(order):
+            o, _ = by_id[id(p)]
+            n = p.numel()
+            state[i] = {"step": torch.tensor(step, dtype=torch.float32),
+                        "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {"lr": float(self.lr), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(order)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, opt):
+        """Accepts a `torch.optim.Adam` state_dict over the getoptim parameter order (what the reference saves and
+        what `optimizer_state_dict` writes) or the round-1 flat layout {step, lr, exp_avg, exp_avg_sq}. Raises when
+        the state does not fit the model instead of silently restarting the moments."""
+        if not opt:
+            return
+        with torch.no_grad():
+            if "param_groups" in opt:
+                order = self.model.trainable_parameters()
+                ids = [i for g in opt["param_groups"] for i in g["params"]]
+                if len(ids) != len(order):
+                    raise RuntimeError("optimizer state covers %d parameters, the model has %d" % (len(ids), len(order)))
+                by_id = {id(p): o for p, o in zip(self.flat.params, self.flat.offsets)}
+                steps = set()
+                for i, p in zip(ids, order):
+                    st = opt["state"].get(i)
+                    if st is None:                       # parameter that never received a gradient
+                        continue
+                    if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                        raise RuntimeError("optimizer state %d has shape %s, parameter has %s" %
+                                           (i, tuple(st["exp_avg"].shape), tuple(p.shape)))
+                    o, n = by_id[id(p)], p.numel()
+                    self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(float(st["step"]))
+                if len(steps) > 1:
+                    raise RuntimeError("per-parameter Adam step counts differ (%s): not a getoptim checkpoint" % sorted(steps))
+                self.opt_state[0] = steps.pop() if steps else 0.0
+                self.set_lr(float(opt["param_groups"][0]["lr"]))
+            elif "exp_avg" in opt:
+                if opt["exp_avg"].numel() != self.exp_avg.numel():
+                    raise RuntimeError("flat optimizer state has %d elements, expected %d" %
+                                       (opt["exp_avg"].numel(), self.exp_avg.numel()))
+                self.exp_avg.copy_(opt["exp_avg"])
+                self.exp_avg_sq.copy_(opt["exp_avg_sq"])
+                self.opt_state[0] = float(opt.get("step", 0))
+                self.set_lr(float(opt.get("lr", self.lr)))
+            else:
+                raise RuntimeError("unknown optimizer_state_dict layout: keys %s" % sorted(opt))
+
     def state_dict(self):
         m = self.model
         return {"encgeo_state_dict": m.net_geoenc.state_dict(), "decgeo_state_dict": m.net_geodec.state_dict(),
                 "mcvcoeffsdec_dict": m.mcvcoeffsdec.state_dict(), "mcvcoeffsenc_dict": m.mcvcoeffsenc.state_dict(),
-                "optimizer_state_dict": {"step": self.step_count, "lr": self.lr, "exp_avg": self.exp_avg,
-                                         "exp_avg_sq": self.exp_avg_sq}}
+                "optimizer_state_dict": self.optimizer_state_dict()}
 
     def save(self, folder, iteration):
-        """Writes `model_%07d_best.weight` exactly as the reference does (graphVAE_train.py:341-347)."""
+        """Writes `model_%07d_best.weight` exactly as the reference does (graphVAE_train.py:341-347), optimizer
+        state included in torch.optim.Adam's own layout."""
         os.makedirs(folder, exist_ok=True)
         path = os.path.join(folder, "model_%07d" % iteration + "_best.weight")
         torch.save(self.state_dict(), path)
         return path
 
     def load(self, path):
-        """Loads a checkpoint written by this trainer or by the reference (its optimizer state, a
-        torch.optim.Adam state_dict over per-tensor moments, is not converted: moments restart at zero)."""
-        ckpt = torch.load(path, map_location=self.flat.flat_p.device)
+        """Loads a checkpoint written by this trainer or by the reference (graphVAE_train.py:284-291): the four
+        module state dicts and the Adam state (moments, step count, learning rate)."""
+        ckpt = torch.load(path, map_location=self.flat.flat_p.device, weights_only=False)
         self.load_model_state(ckpt)
-        opt = ckpt.get("optimizer_state_dict", {})
-        if "exp_avg" in opt and opt["exp_avg"].numel() == self.exp_avg.numel():
-            with torch.no_grad():
-                self.exp_avg.copy_(opt["exp_avg"])
-                self.exp_avg_sq.copy_(opt["exp_avg_sq"])
-                self.opt_state[0] = float(opt.get("step", 0))
-                self.set_lr(float(opt.get("lr", self.lr)))
+        self.load_optimizer_state_dict(ckpt.get("optimizer_state_dict"))
         return ckpt
 
     def fit(self, param, epochs_of_batches, log=None, gamma=0.99):
