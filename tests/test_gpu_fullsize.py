@@ -99,7 +99,11 @@ def _cuda_step(model, pc, nor, eps, precision):
 def _compare(tag, got, want, tol_out, tol_loss, tol_grad):
     (v, g), (v0, g0) = got, want
     e_out = rel_err(v["out"], v0["out"])
-    e_loss = {k: abs(v[k] - v0[k]) / max(abs(v0[k]), 1e-12) for k in ("loss", "l1", "laplace", "kl", "normal")}
+    # The KL term (graphVAE_train.py:206) is a mean of -0.5 - logstd + 0.5 mu^2 + 0.5 exp(2 logstd): O(0.5) terms that
+    # cancel to ~1e-6 at initialisation, so its fp32 evaluation (the reference's included) carries an ABSOLUTE rounding
+    # error of ~1e-8; it is measured against a floor of 1e-3 (it enters the loss with weight 1e-5).
+    floor = {"kl": 1e-3}
+    e_loss = {k: abs(v[k] - v0[k]) / max(abs(v0[k]), floor.get(k, 1e-12)) for k in ("loss", "l1", "laplace", "kl", "normal")}
     e_grad = {k: rel_err(g[k], g0[k]) for k in g0}
     worst = max(e_grad, key=e_grad.get)
     _record(tag, {"out": e_out, "loss_parts": e_loss, "worst_grad": {"param": worst, "err": e_grad[worst]},
@@ -156,10 +160,11 @@ def test_c2_graph_replay_equals_eager_step(c2):
     """What bench.py times is the CUDA-graph replay of the step: same parameters after a step as the eager step
     whose gradients the tests above hold to the oracle."""
     model, pc, nor, eps, _ = c2
-    import copy
     prev = F_.set_precision("tf32")
     try:
-        m1, m2 = copy.deepcopy(model), copy.deepcopy(model)
+        m1, m2 = (T.build_synthetic_autoencoder(6890)[0].cuda() for _ in range(2))
+        m1.load_state_dict(model.state_dict())
+        m2.load_state_dict(model.state_dict())
         t1, t2 = T.DataParallelTrainer(m1, lr=1e-4), T.DataParallelTrainer(m2, lr=1e-4)
         t2.capture(pc, nor, warmup=0)
         for _ in range(2):

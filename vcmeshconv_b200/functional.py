@@ -54,12 +54,14 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def _grad_target(t):
+def _grad_target(t, needed=True):
     """Slice of the trainer's flat gradient buffer registered for parameter `t` (or for the parameter `t`
     is a whole, order-preserving view of), if this is the first gradient written to it this step. The
     backward kernels then write there directly and autograd sees no gradient for the input: no temporary,
-    no accumulate kernel, and the buffer NCCL reduces / Adam reads is filled in place."""
-    if t is None or not torch.is_grad_enabled():
+    no accumulate kernel, and the buffer NCCL reduces / Adam reads is filled in place. `needed` is the
+    Function's `ctx.needs_input_grad[k]` of that input: False under no_grad at the call site (grad mode is always off
+    INSIDE Function.forward, so it cannot be asked there), and then nothing is claimed."""
+    if t is None or not needed:
         return None
     base = t._base if t._base is not None else t
     buf = getattr(base, "_vcm_grad_buf", None)
@@ -96,7 +98,7 @@ class _GatherContract(torch.autograd.Function):
         ctx.save_for_backward(x, A)
         ctx.tables = tables
         ctx.precision = _precision
-        ctx.dA_target = _grad_target(A) if A.requires_grad else None
+        ctx.dA_target = _grad_target(A, ctx.needs_input_grad[1])
         return z
 
     @staticmethod
@@ -171,7 +173,7 @@ class _ProjectGather(torch.autograd.Function):
                   tag="P%d>%d MO%d" % (tables.p_in, tables.p_out, M * O))
         ctx.save_for_backward(u, A)
         ctx.tables, ctx.cfg = tables, (M, O)
-        ctx.dA_target = _grad_target(A) if A.requires_grad else None
+        ctx.dA_target = _grad_target(A, ctx.needs_input_grad[1])
         return s
 
     @staticmethod
@@ -243,8 +245,8 @@ class _BasisGemm(torch.autograd.Function):
         y_saved = (y_act if y_act is not None else out) if act else None
         ctx.save_for_backward(z, W, y_saved)
         ctx.cfg = (M, I, O, int(act), scale_y, scale_res, precision, per_point, bias is not None, res is not None)
-        ctx.dW_target = _grad_target(W) if W.requires_grad else None
-        ctx.db_target = _grad_target(bias) if bias is not None and bias.requires_grad else None
+        ctx.dW_target = _grad_target(W, ctx.needs_input_grad[1])
+        ctx.db_target = _grad_target(bias, ctx.needs_input_grad[2])
         ctx.Wt = None
         if _prep_stream is not None and ctx.needs_input_grad[0] and B and p_out:
             # the dz GEMM's stacked-bases operand depends on W only: built now, on the trainer's preparation
@@ -419,9 +421,9 @@ class _FusedConv(torch.autograd.Function):
         ctx.save_for_backward(x, A, W, z, y_saved)
         ctx.tables = tables
         ctx.cfg = (M, I, O, int(act), scale_y, scale_res, precision, per_point, bias is not None, res is not None)
-        ctx.dA_target = _grad_target(A) if A.requires_grad else None
-        ctx.dW_target = _grad_target(W) if W.requires_grad else None
-        ctx.db_target = _grad_target(bias) if bias is not None and bias.requires_grad else None
+        ctx.dA_target = _grad_target(A, ctx.needs_input_grad[1])
+        ctx.dW_target = _grad_target(W, ctx.needs_input_grad[2])
+        ctx.db_target = _grad_target(bias, ctx.needs_input_grad[3])
         return out
 
     @staticmethod
@@ -461,7 +463,7 @@ class _BiasAct(torch.autograd.Function):
                       tag="R%d O%d" % (B * p_out, O))
         ctx.save_for_backward((y_act if y_act is not None else out) if act else None)
         ctx.cfg = (int(act), scale_y, scale_res, per_point, bias is not None, res is not None, O)
-        ctx.db_target = _grad_target(bias) if bias is not None and bias.requires_grad else None
+        ctx.db_target = _grad_target(bias, ctx.needs_input_grad[1])
         return out
 
     @staticmethod
@@ -502,7 +504,7 @@ class _EdgeWeights(torch.autograd.Function):
                   nbytes=12 * p_nb.numel(), flops=3 * p_nb.numel())
         ctx.save_for_backward(p_nb)
         ctx.tables = tables
-        ctx.dp_target = _grad_target(p_nb) if p_nb.requires_grad else None
+        ctx.dp_target = _grad_target(p_nb, ctx.needs_input_grad[0])
         return pn
 
     @staticmethod

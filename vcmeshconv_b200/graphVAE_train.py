@@ -420,9 +420,15 @@ class DataParallelTrainer:
         lo, hi = self._early_upto, self.early_bounds[i]
         s = self.early_stream
         s.wait_stream(torch.cuda.current_stream())
+        capturing = torch.cuda.is_current_stream_capturing()
         for st in (F_._side_stream, F_._da_stream, self.res_stream):
-            if st is not None:
-                s.wait_stream(st)
+            if st is None:
+                continue
+            if capturing:
+                with torch.cuda.stream(st):              # a branch stream that got no work inside this capture has
+                    if not torch.cuda.is_current_stream_capturing():    # nothing to wait for (and may not be waited on)
+                        continue
+            s.wait_stream(st)
         with torch.cuda.stream(s):
             if self.world > 1:
                 self._allreduce(lo, hi)
