@@ -142,8 +142,9 @@ VCM_API int vcm_coeff_grad(const vcm_tables *t, const float *dz, const float *x,
 /* Same gradients with the arithmetic mode of the basis GEMMs: in VCM_PREC_TF32 / VCM_PREC_TF32X3 both are small
  * per-vertex GEMMs on the tensor pipe (mma.sync m16n8k8 tf32; TF32X3 = hi/lo split, fp32-grade) when M <= 24,
  * I % 16 == 0 and N <= 64; every other case is the fp32 kernel above. Use the matching workspace query. */
-/* Diagnostics: which kernel vcm_coeff_grad_ex runs for this shape: 1 = tensor-pipe kernel
- * (coeff_grad_mma_kernel), 0 = fp32 CUDA-core kernel (coeff_grad_kernel). bench.py groups its timings by it. */
+/* Diagnostics: which kernel vcm_coeff_grad_ex runs for this shape: 2 = tensor-pipe kernel with TMA-staged dz tiles
+ * and an mbarrier pipeline (coeff_grad_tma_kernel, the TF32-mode default), 1 = tensor-pipe kernel staged with
+ * cp.async (coeff_grad_mma_kernel), 0 = fp32 CUDA-core kernel (coeff_grad_kernel). bench.py groups its timings by it. */
 VCM_API int vcm_coeff_grad_variant(const vcm_tables *t, int B, int I, int M, int precision);
 VCM_API size_t vcm_coeff_grad_workspace_ex(const vcm_tables *t, int B, int I, int M, int precision);
 VCM_API int vcm_coeff_grad_ex(const vcm_tables *t, const float *dz, const float *x, const float *A, float *dA,

@@ -1,0 +1,58 @@
+"""K1 with shared-memory staged neighbour rows on the tensor pipe (csrc/gather_fwd_tile.cu; the TF32-mode default of
+vcm_gather_contract_fwd_ex): z[b,p,m,i] = sum_n A[p,n,m] x[b,idx[p,n],i]  (graphVAESSW.py:111-123).
+
+Exact (<= 2e-5) against the fp64 contraction of TF32-truncated operands -- pins the staging layout, the permuted k
+slots and the fragment mapping independently of rounding --, within the stated TF32 tolerance (3e-3) of the fp32
+kernel, bitwise reproducible, no NaN from padding rows, every element of z written."""
+import numpy as np
+import pytest
+import torch
+
+from test_gpu_fused import random_table, rel_err, trunc_tf32
+from vcmeshconv_b200 import _lib
+from vcmeshconv_b200.connectivity import DeviceTables
+
+pytestmark = pytest.mark.gpu
+TF32 = _lib.PRECISIONS["tf32"]
+
+CASES = [  # B, p_in, p_out, n_max, M, I
+    (16, 60, 45, 7, 17, 32),            # one k-step
+    (16, 344, 300, 12, 17, 128),        # unpool-like, two k-steps, several units per warp
+    (16, 200, 200, 20, 17, 64),         # degree buckets: > 16 neighbours -> 4-step kernel, the rest 2-step
+    (16, 100, 20, 31, 17, 256),         # few vertices, many units per vertex
+    (3, 50, 40, 9, 17, 32),             # odd batch
+    (1, 50, 40, 9, 17, 64),
+    (16, 90, 33, 58, 17, 64),           # pooling-like: 8 k-steps
+    (8, 64, 64, 6, 9, 64),              # M = 9: one basis tile
+    (16, 64, 64, 6, 24, 32),            # M = 24 fills the second basis tile
+    (2, 30, 25, 5, 16, 512),            # M = 16, wide rows
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_P%d-%d_N%d_M%d_I%d" % c)
+def test_gather_contract_tile_kernel(case):
+    B, p_in, p_out, n_max, M, I = case
+    tab, ids = random_table(p_in, p_out, n_max, seed=p_out + n_max)
+    t = DeviceTables(tab, p_in)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(B, p_in, I, device="cuda", generator=g)
+    A = torch.randn(p_out, n_max, M, device="cuda", generator=g)
+    A[torch.from_numpy(ids == p_in).cuda()] = float("nan")          # padded coefficient slots must never be read as data
+    L = _lib.lib()
+    z = torch.full((B, p_out, M * I), float("nan"), device="cuda")
+    z2 = torch.full_like(z, float("nan"))
+    z32 = torch.empty_like(z)
+    for out in (z, z2):
+        _lib.check(L.vcm_gather_contract_fwd_ex(t.handle, x.data_ptr(), A.data_ptr(), out.data_ptr(), B, I, M, TF32,
+                                                _lib.stream_ptr()))
+    _lib.check(L.vcm_gather_contract_fwd(t.handle, x.data_ptr(), A.data_ptr(), z32.data_ptr(), B, I, M, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    idt = torch.from_numpy(ids).cuda()
+    real = (idt != p_in)
+    A0 = torch.where(real[:, :, None], A, torch.zeros_like(A))
+    xpad = torch.cat([trunc_tf32(x).double(), torch.zeros(B, 1, I, device="cuda", dtype=torch.float64)], 1)
+    want = torch.einsum("pnm,bpni->bpmi", trunc_tf32(A0).double(), xpad[:, idt]).reshape(B, p_out, M * I)
+    assert torch.isfinite(z).all()                                   # every element written, no NaN from padding
+    assert torch.equal(z, z2)                                        # bitwise reproducible
+    assert rel_err(z, want) < 2e-5
+    assert rel_err(z, z32) < 3e-3

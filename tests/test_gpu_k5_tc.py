@@ -70,7 +70,7 @@ def test_coeff_grad_tensor_pipe(case, prec):
     tol = 3e-3 if prec == "tf32" else 1e-5
     assert rel_err(dA, wA) < tol
     assert rel_err(dGm, wG) < tol
-    if prec == "tf32" and n_max <= 32 and M >= 2 and I % 32 == 0:
+    if prec == "tf32" and n_max <= 64 and M >= 2 and I % 32 == 0:
         # the tensor-pipe kernel ran: it must match the product of truncated operands to accumulation round-off
         tA, tG, _ = reference(trunc_tf32(dz), trunc_tf32(x), trunc_tf32(A), ids, p_in)
         assert rel_err(dA, tA) < 2e-5

@@ -80,6 +80,7 @@ def main():
     for _ in range(a.iters):
         flush.zero_()                               # evict L2 between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(400000)                   # the launch below is queued before the stream reaches e0
         e0.record()
         _lib.check(fn())
         e1.record()

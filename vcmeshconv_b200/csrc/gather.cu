@@ -17,6 +17,8 @@
 // zero-padded copy of x. All reductions have a fixed order: results are
 // bitwise reproducible and there are no atomics.
 #include "common.cuh"
+#include "k1_tile.h"
+#include "k5_tma.h"
 
 namespace vcm {
 
@@ -322,6 +324,11 @@ __global__ void sum_splits_kernel(const float *__restrict__ part, float *__restr
     float s = 0.f;
     for (int k = 0; k < n_split; ++k) s += part[(size_t)k * n + i];
     out[i] = s;
+}
+
+void launch_sum_splits(const float *part, float *out, size_t n, int n_split, cudaStream_t st) {
+    sum_splits_kernel<<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, st>>>(part, out, n, n_split);
+    count_launch();
 }
 
 // ------------------------------------------------------------------ K6 ------
@@ -962,6 +969,15 @@ extern "C" int vcm_gather_contract_fwd_ex(const vcm_tables *h, const float *x, c
                                           int M, int precision, void *stream) {
     using namespace vcm;
     const Tables *t = as_tables(h);
+    {
+        // TF32 mode default: shared-memory staged neighbour rows + mma.sync (csrc/gather_fwd_tile.cu)
+        K1TilePlan tp;
+        if (k1_tile_plan(t, B, I, M, precision, &tp)) {
+            VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR(z);
+            if (int e0 = check_common(t, B, I, M)) return e0;
+            return k1_tile_launch(t, tp, x, A, z, B, I, M, (cudaStream_t)stream);
+        }
+    }
     // opt-in: correct (tests/test_gpu_gemm_tc.py) but measured 1.5 % slower than the fp32 kernel in the full
     // training step (3.675 vs 3.618 ms, same box): K1 is bound by its memory system, not by the FMA pipe
     static const int use_mma = [] { const char *e = getenv("VCM_K1_MMA"); return e ? atoi(e) : 0; }();
@@ -1408,6 +1424,11 @@ size_t vcm_coeff_grad_workspace_ex(const vcm_tables *h, int B, int I, int M, int
         const size_t n = (size_t)pl.gy * t->p_out * t->n_max * M;
         need = n > need ? n : need;
     }
+    K5TmaPlan tp;
+    if (k5_tma_plan(t, B, I, M, precision, &tp)) {
+        const size_t n = k5_tma_workspace(t, tp, M);
+        need = n > need ? n : need;
+    }
     return need;
 }
 
@@ -1424,6 +1445,8 @@ static bool use_grad_mma(const vcm::Tables *t, int B, int I, int M, int precisio
 
 int vcm_coeff_grad_variant(const vcm_tables *h, int B, int I, int M, int precision) {
     vcm::MmaGradPlan pl;
+    vcm::K5TmaPlan tp;
+    if (vcm::k5_tma_plan(vcm::as_tables(h), B, I, M, precision, &tp)) return 2;
     return use_grad_mma(vcm::as_tables(h), B, I, M, precision, &pl) ? 1 : 0;
 }
 
@@ -1432,6 +1455,13 @@ int vcm_coeff_grad_ex(const vcm_tables *h, const float *dz, const float *x, cons
     using namespace vcm;
     const Tables *t = as_tables(h);
     MmaGradPlan pl;
+    K5TmaPlan tp;
+    if (k5_tma_plan(t, B, I, M, precision, &tp)) {
+        VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR_OPT(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
+        VCM_CHECK(dA != nullptr || dG != nullptr, "nothing to compute: dA and dG are both NULL");
+        if (int e0 = check_common(t, B, I, M)) return e0;
+        return k5_tma_launch(t, tp, dz, x, A, dA, dG, ws, B, I, M, (cudaStream_t)stream);
+    }
     if (!use_grad_mma(t, B, I, M, precision, &pl)) return vcm_coeff_grad(h, dz, x, A, dA, dG, ws, B, I, M, stream);
     VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR_OPT(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
     VCM_CHECK(dA != nullptr || dG != nullptr, "nothing to compute: dA and dG are both NULL");

@@ -1,0 +1,323 @@
+// K1 (stage 1 of the vc-conv forward, graphVAESSW.py:111-123) on the tensor pipe with shared-memory staged
+// neighbour rows (TF32 mode):
+//
+//   z[b,p,m,i] = sum_n A[p,n,m] x[b,idx[p,n],i]
+//
+// One CTA = one output vertex (processing order, degree buckets) x a share of its UNITS; a unit is one batch entry x
+// CW consecutive channels. Per unit the warp stages the vertex's neighbour rows x[idx[p,n]][CW] in shared memory with
+// 16-byte cp.async pieces (a per-row gather of 128/256-byte segments: 128-bit coalesced loads, the index pattern has no
+// box for TMA), S units deep (cp.async groups; the warp that waits on a stage is the warp that refills it), and
+// contracts on mma.sync m16n8k8 (tf32 operands, fp32 accumulate):
+//
+//   z_unit[m][c] = AT[m][n] x[n][c]      M = bases (two 16-row tiles for 17 <= M <= 24), N = 8 columns, K = neighbours
+//
+// The coefficient fragments AT (per vertex, constant over its units) live in registers (<= 16 neighbours) or are
+// re-read from the shared tile once per unit. The x fragments need x[n][c] with k = n, i.e. the transposed access:
+// scalar LDS, made bank-conflict-free by PERMUTING the k slots (slot j of an 8-group holds neighbour 2j, slot j+4
+// neighbour 2j+1: lane (g,t) reads rows 2t, 2t+1, column g; with rows padded by 16 bytes the 32 lanes hit 32 banks);
+// every address is one per-unit base plus immediates. Results leave as 8-byte stores, 32 bytes per row segment.
+// Padding neighbours meet a zero coefficient and a zeroed row. Per 32-column unit of an 8-neighbour vertex: ~65 warp
+// instructions for 2176 bytes of z (the fp32 kernel: ~320 per 1088 bytes).
+#include "common.cuh"
+#include "k1_tile.h"
+#include "tc_common.cuh"
+
+namespace vcm {
+namespace {
+
+constexpr int kW = 4;              // warps per CTA
+
+struct K1Params {
+    const int32_t *idx_sorted;
+    const int2 *meta_sorted;
+    const float *x, *A;
+    float *z;
+    int p_in, p_out, n_max, I, M, B;
+    int units_per_cta, slot0, stages, cpi_shift;
+};
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t lds32_o(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+// 16-byte cp.async, skipped when off == 0xFFFFFFFF (predicated inside the asm: no branch around it)
+template <int DOFF>
+__device__ __forceinline__ void cp16_if(uint32_t dst, const char *base, uint32_t off) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+        "setp.ne.u32 p, %2, 0xFFFFFFFF;\n\t"
+        "cvt.u64.u32 a, %2;\n\t"
+        "add.u64 a, a, %1;\n\t"
+        "@p cp.async.cg.shared.global [%0+%3], [a], 16;\n\t}"
+        ::"r"(dst), "l"(base), "r"(off), "n"(DOFF) : "memory");
+}
+__device__ __forceinline__ void cp_wait_all_but(int n) {            // n is warp-uniform
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    }
+}
+template <int K0, int K1, int STEP, int N>
+__device__ __forceinline__ void x_rounds(uint32_t dst, const char *xb, const uint32_t (&xq)[N]) {
+    if constexpr (K0 < K1) {
+        cp16_if<K0 * STEP>(dst, xb, xq[K0]);
+        x_rounds<K0 + 1, K1, STEP, N>(dst, xb, xq);
+    }
+}
+
+// NK = 8-neighbour k-steps (vertices of this launch have at most 8*NK neighbours), CW = columns per unit, MT = 16-row
+// basis tiles (1: M <= 16, 2: M <= 24 -- rows 24..31 of the second tile do not exist and are never stored)
+template <int NK, int CW, int MT>
+__global__ void __launch_bounds__(32 * kW, NK <= 2 ? 4 : 2)
+gather_fwd_tile_kernel(const K1Params P) {
+    constexpr int NP = NK * 8;
+    constexpr int RSB = (CW + 4) * 4;             // x row stride in bytes
+    constexpr int PIECES = CW / 4, RPR = 32 / PIECES, XR = NP / RPR, XK = XR < 8 ? XR : 8;
+    constexpr int ATS = NP + 4;                   // coefficient tile row stride (words): conflict-free ldmatrix
+    constexpr bool KEEP = NK <= 2;
+    constexpr int STAGE = NP * RSB;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3, lr = lane & 7, lj = lane >> 3;
+    const int S = P.stages, M = P.M, I = P.I;
+    float *AT_s = reinterpret_cast<float *>(smem_raw + (size_t)kW * S * STAGE);   // [MT*16][ATS], k slots permuted
+    int32_t *idx_s = reinterpret_cast<int32_t *>(AT_s + MT * 16 * ATS);            // [NP]
+    float *raw_s = reinterpret_cast<float *>(idx_s + NP);                          // [l][M] as stored
+    const uint32_t my_ring = smem_u32(smem_raw) + (uint32_t)(warp * S) * STAGE;
+
+    const int slot = blockIdx.x + P.slot0;
+    const int2 meta = __ldg(P.meta_sorted + slot);
+    const int p = meta.x, l = meta.y;
+    const int total_units = P.B << P.cpi_shift, cpi_mask = (1 << P.cpi_shift) - 1;
+    const int u_begin = blockIdx.y * P.units_per_cta;
+    const int u_end = min(total_units, u_begin + P.units_per_cta);
+
+    for (int n = tid; n < NP; n += blockDim.x) {
+        const int q = n < l ? __ldg(P.idx_sorted + (size_t)slot * P.n_max + n) : P.p_in;
+        idx_s[n] = q == P.p_in ? -1 : q;
+    }
+    {
+        const float *Ap = P.A + (size_t)p * P.n_max * M;
+        for (int e = tid; e < l * M; e += blockDim.x) raw_s[e] = __ldg(Ap + e);
+    }
+    __syncthreads();
+
+    // rows of the ring that no copy will ever write (padding neighbours) must be finite: zero them once
+    for (int s = 0; s < S; ++s)
+        for (int e = lane; e < NP * PIECES; e += 32) {
+            const int n = e / PIECES, j = e - n * PIECES;
+            if (idx_s[n] < 0)
+                *reinterpret_cast<float4 *>(smem_raw + (size_t)(warp * S + s) * STAGE + n * RSB + j * 16) =
+                    make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+
+    // x rows of a unit: round k of the warp covers rows k*RPR .. k*RPR+RPR-1, lane -> (row, 16-byte piece)
+    const int xr0 = lane / PIECES, xj = lane % PIECES;
+    const uint32_t x_dst0 = (uint32_t)(xr0 * RSB + xj * 16);
+    const uint32_t row_bytes = (uint32_t)I * 4u;                     // q * row_bytes < 2^32 (checked by the plan)
+    uint32_t xq[XK];
+#pragma unroll
+    for (int k = 0; k < XK; ++k) {
+        const int q = idx_s[k * RPR + xr0];
+        xq[k] = q >= 0 ? (uint32_t)q * row_bytes : 0xFFFFFFFFu;
+    }
+    auto issue = [&](int u, int s) {
+        const int b = u >> P.cpi_shift, ch = u & cpi_mask;
+        const char *xb = reinterpret_cast<const char *>(P.x + (size_t)b * P.p_in * I + ch * CW + xj * 4);
+        asm volatile("" : "+l"(xb));                                 // one 64-bit base per unit, not one per piece
+        const uint32_t dst = my_ring + (uint32_t)s * STAGE + x_dst0;
+        if (XK <= 2 || l > 2 * RPR) {                                // warp-uniform
+            x_rounds<0, XK, RPR * RSB, XK>(dst, xb, xq);
+        } else {
+            x_rounds<0, (XK < 2 ? XK : 2), RPR * RSB, XK>(dst, xb, xq);
+        }
+        for (int k = XK; k * RPR < l; ++k) {                         // more than 8 rounds: the pooling layers
+            const int q = idx_s[k * RPR + xr0];
+            if (q >= 0) {
+                const char *src = xb + (uint32_t)q * row_bytes;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(k * RPR * RSB)), "l"(src) : "memory");
+            }
+        }
+    };
+    int u = u_begin + warp;                                          // unit being multiplied
+    int u_issue = u;                                                 // next unit to request
+    __syncwarp();
+    for (int s = 0; s < S - 1; ++s, u_issue += kW) {
+        if (u_issue < u_end) issue(u_issue, s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    // coefficient tile AT[m][slot]: slot j of group ks <-> neighbour ks*8 + (j < 4 ? 2j : 2(j-4)+1); zero where the
+    // basis or the neighbour does not exist
+    for (int e = tid; e < MT * 16 * NP; e += blockDim.x) {
+        const int m = e / NP, c = e - m * NP, j = c & 7;
+        const int n = (c & ~7) + (j < 4 ? 2 * j : 2 * (j - 4) + 1);
+        AT_s[m * ATS + c] = (m < M && n < l && idx_s[n] >= 0) ? raw_s[n * M + m] : 0.f;
+    }
+    __syncthreads();
+
+    const uint32_t AT_u = smem_u32(AT_s);
+    const uint32_t c_row_off = (uint32_t)(((lj & 1) * 8 + lr) * ATS + (lj >> 1) * 4) * 4u;
+    uint32_t cT[KEEP ? MT : 1][KEEP ? NK : 1][4];
+    if (KEEP) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < NK; ++ks) ldsm4(cT[mt][ks], AT_u + c_row_off + (uint32_t)(mt * 16 * ATS + ks * 8) * 4u);
+    }
+    const int nks = (l + 7) >> 3;                                    // k-steps this vertex needs (warp-uniform)
+    const uint32_t b_lane = (uint32_t)(2 * t * RSB + g * 4);         // row 2t, column g of a stage
+    const bool st1 = MT > 1 && 16 + g < M;                           // this lane stores a row of the second tile
+    const bool st0b = g + 8 < M, st0a = g < M;
+
+    int stage = 0, fill = S - 1;                                     // stage being multiplied / refilled next
+    for (; u < u_end; u += kW) {
+        cp_wait_all_but(S - 2);                        // the oldest of the S - 1 groups in flight = this unit
+        __syncwarp();
+        if (u_issue < u_end) issue(u_issue, fill);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        u_issue += kW;
+        if (++fill == S) fill = 0;
+
+        const uint32_t xb = my_ring + (uint32_t)stage * STAGE + b_lane;
+        const int b = u >> P.cpi_shift, ch = u & cpi_mask;
+        float *zp = P.z + (((size_t)b * P.p_out + p) * M + g) * I + ch * CW + 2 * t;
+        float *zp8 = zp + (size_t)8 * I, *zp16 = zp + (size_t)16 * I;
+        asm volatile("" : "+l"(zp), "+l"(zp8), "+l"(zp16));
+#pragma unroll
+        for (int c8 = 0; c8 < CW / 8; ++c8) {
+            float d[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < NK; ++ks) {
+                if (NK > 1 && ks >= nks) break;                      // warp-uniform
+                uint32_t b0, b1;
+                switch (ks) {                                        // immediates: ks * 8 rows, the odd row, the column block
+                    case 0: b0 = lds32_o<0 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<0 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    case 1: b0 = lds32_o<1 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<1 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    case 2: b0 = lds32_o<2 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<2 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    case 3: b0 = lds32_o<3 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<3 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    case 4: b0 = lds32_o<4 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<4 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    case 5: b0 = lds32_o<5 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<5 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    case 6: b0 = lds32_o<6 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<6 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    default: b0 = lds32_o<7 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<7 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    if (KEEP) {
+                        mma_tf32(d[mt], cT[mt][ks], b0, b1);
+                    } else {
+                        uint32_t a[4];
+                        ldsm4(a, AT_u + c_row_off + (uint32_t)(mt * 16 * ATS + ks * 8) * 4u);
+                        mma_tf32(d[mt], a, b0, b1);
+                    }
+                }
+            }
+            if (st0a) *reinterpret_cast<float2 *>(zp + c8 * 8) = make_float2(d[0][0], d[0][1]);
+            if (st0b) *reinterpret_cast<float2 *>(zp8 + c8 * 8) = make_float2(d[0][2], d[0][3]);
+            if (MT > 1 && st1) *reinterpret_cast<float2 *>(zp16 + c8 * 8) = make_float2(d[MT - 1][0], d[MT - 1][1]);
+        }
+        if (++stage == S) stage = 0;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+size_t cta_smem(int nk, int cw, int mt, int stages, int M) {
+    const int np = nk * 8;
+    return (size_t)kW * stages * np * (cw + 4) * 4 + (size_t)mt * 16 * (np + 4) * 4 + (size_t)np * 4 + (size_t)np * M * 4 + 16;
+}
+
+template <int NK, int CW, int MT>
+int launch_bucket(const Tables *t, const K1TilePlan &pl, K1Params P, int n_slots, cudaStream_t st) {
+    if (n_slots <= 0) return VCM_OK;
+    int stages = pl.stages;
+    while (stages > 2 && cta_smem(NK, CW, MT, stages, P.M) > 56 * 1024) --stages;
+    P.stages = stages;
+    const size_t smem = cta_smem(NK, CW, MT, stages, P.M);
+    auto k = gather_fwd_tile_kernel<NK, CW, MT>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        VCM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)n_slots, (unsigned)pl.gy);
+    k<<<grid, 32 * kW, smem, st>>>(P);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+// Degree buckets of the processing order (vertices sorted by neighbour count, descending): slots [0, n_gt16) run the
+// kernel sized for the table width, the rest the 16-neighbour kernel.
+template <int CW, int MT>
+int launch_all(const Tables *t, const K1TilePlan &pl, K1Params P, cudaStream_t st) {
+    const int n_hi = pl.nk > 2 ? t->n_gt16 : 0;
+    int e = VCM_OK;
+    P.slot0 = 0;
+    if (pl.nk > 4) e = launch_bucket<8, CW, MT>(t, pl, P, n_hi, st);
+    else if (pl.nk > 2) e = launch_bucket<4, CW, MT>(t, pl, P, n_hi, st);
+    if (e) return e;
+    P.slot0 = n_hi;
+    if (pl.nk == 1) return launch_bucket<1, CW, MT>(t, pl, P, t->p_out - n_hi, st);
+    return launch_bucket<2, CW, MT>(t, pl, P, t->p_out - n_hi, st);
+}
+
+}  // namespace
+
+bool k1_tile_plan(const Tables *t, int B, int I, int M, int precision, K1TilePlan *pl) {
+    static const int enabled = tune_flag("VCM_K1_TILE", 1);
+    if (!enabled || precision != VCM_PREC_TF32 || t == nullptr || B <= 0 || t->p_out == 0) return false;
+    if (M < 2 || M > 24 || I % 32 != 0 || t->n_max > 64) return false;
+    const int cpi32 = I / 32;
+    if ((cpi32 & (cpi32 - 1)) != 0) return false;
+    if ((int64_t)t->p_in * I * 4 >= (int64_t)1 << 32) return false;
+    pl->nk = (t->n_max + 7) / 8;
+    pl->cw = (I % 64 == 0) ? tune_flag("VCM_K1_CW", 32) : 32;
+    if (pl->cw != 32 && pl->cw != 64) pl->cw = 32;
+    pl->stages = tune_flag("VCM_K1_STAGES", 3);
+    if (pl->stages < 2) pl->stages = 2;
+    if (pl->stages > 8) pl->stages = 8;
+    const int units = B * (I / pl->cw);
+    int64_t want = ceil_div((int64_t)tune_flag("VCM_K1_CTAS_PER_SM", 8) * sm_count(), t->p_out);
+    const int64_t max_gy = ceil_div(units, (int64_t)kW * 4);
+    if (want > max_gy) want = max_gy;
+    if (want < 1) want = 1;
+    pl->units_per_cta = (int)(ceil_div(ceil_div(units, want), kW) * kW);
+    pl->gy = (int)ceil_div(units, pl->units_per_cta);
+    return true;
+}
+
+int k1_tile_launch(const Tables *t, const K1TilePlan &pl, const float *x, const float *A, float *z, int B, int I, int M,
+                   cudaStream_t st) {
+    if (!aligned16(x) || (reinterpret_cast<uintptr_t>(z) & 7) != 0) return fail(VCM_EINVAL, "x must be 16-byte, z 8-byte aligned");
+    K1Params P;
+    P.idx_sorted = t->idx_sorted;
+    P.meta_sorted = reinterpret_cast<const int2 *>(t->meta_sorted);
+    P.x = x; P.A = A; P.z = z;
+    P.p_in = t->p_in; P.p_out = t->p_out; P.n_max = t->n_max; P.I = I; P.M = M; P.B = B;
+    P.units_per_cta = pl.units_per_cta; P.slot0 = 0; P.stages = pl.stages;
+    int sh = 0;
+    while ((1 << sh) < I / pl.cw) ++sh;
+    P.cpi_shift = sh;
+    if (pl.cw == 64) return M <= 16 ? launch_all<64, 1>(t, pl, P, st) : launch_all<64, 2>(t, pl, P, st);
+    return M <= 16 ? launch_all<32, 1>(t, pl, P, st) : launch_all<32, 2>(t, pl, P, st);
+}
+
+}  // namespace vcm

@@ -55,6 +55,35 @@ def tets(n_vert, seed=0):
     return pts.astype(np.float32), np.ascontiguousarray(faces, dtype=np.int32)
 
 
+def tets_capped(n_vert, max_count=32, seed=0):
+    """Config C5: the tetrahedral template with the neighbour count (self included, as the connectivity tables count
+    it) capped at `max_count`. Delaunay tets are taken in sorted order and a tet is kept only if none of its four
+    vertices would get more than max_count - 1 distinct neighbours: an irregular, non-manifold tet complex (holes
+    where hub vertices were saturated) whose radius-1 table has N_max = max_count exactly when the cap binds."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n_vert, 3))
+    t = Delaunay(pts).simplices.astype(np.int32)
+    t = t[np.lexsort((t[:, 3], t[:, 2], t[:, 1], t[:, 0]))]
+    adj = [set() for _ in range(n_vert)]
+    keep = np.zeros(len(t), dtype=bool)
+    cap = max_count - 1
+    for k, tet in enumerate(t.tolist()):
+        ok = True
+        for v in tet:
+            a = adj[v]
+            if len(a) + sum(1 for w in tet if w != v and w not in a) > cap:
+                ok = False
+                break
+        if ok:
+            keep[k] = True
+            for v in tet:
+                adj[v].update(w for w in tet if w != v)
+    t = t[keep]
+    faces = np.concatenate([t[:, [0, 1, 2]], t[:, [0, 1, 3]], t[:, [0, 2, 3]], t[:, [1, 2, 3]]])
+    return pts.astype(np.float32), np.ascontiguousarray(faces, dtype=np.int32)
+
+
 def write_obj(path, pts, faces, green=()):
     """OBJ with per-vertex colour, the input format of the reference tool
     (GraphSampling/meshLoader.h:221-330: 'v x y z r g b', 'f a b c', 1-based).
