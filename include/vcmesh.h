@@ -291,6 +291,23 @@ VCM_API int vcm_loss_head_bwd(const vcm_tables *lap, const vcm_tables *faces, co
                               const float *g_total, float *d_out, int B, float w_pose, float w_lap, float w_nor,
                               void *stream);
 
+/* ------------------------------------------------- data-parallel reduction --
+ * Gradient SUM over the ranks of one node fused with the optimizer, over NVLink peer memory (replaces the
+ * reduce-to-GPU-0 + Adam of nn.DataParallel, graphVAE_train.py:277, 315-316). grad_peers / param_peers / flag_peers
+ * are HOST arrays of `world` DEVICE pointers: the base of every rank's flat gradient, flat parameter and flag buffer
+ * as mapped into THIS process (symmetric memory). For the range [offset, offset + n) one kernel does: barrier; for
+ * the chunks this rank owns (chunk c = elements [c*chunk, (c+1)*chunk) of the flat buffers belongs to rank
+ * c % world) sum the ranks' gradients in rank order, apply Adam (exp_avg / exp_avg_sq are this rank's own buffers,
+ * live on its chunks only; opt_state = {step, lr, 1-b1^t, sqrt(1-b2^t)} on the device, see vcm_adam_advance) and
+ * store the new parameters into every rank's parameter buffer; barrier. Flag buffer: uint32, zero-initialised, at
+ * least 8 * (flag_slot + vcm_reduce_adam_blocks(n, world)) entries; concurrent launches must use disjoint slots and
+ * every rank must issue the same launches in the same order. */
+VCM_API int vcm_reduce_adam_chunk(void);
+VCM_API int vcm_reduce_adam_blocks(size_t n, int world);
+VCM_API int vcm_reduce_adam_bcast(const float *const *grad_peers, float *const *param_peers, uint32_t *const *flag_peers,
+                                  float *exp_avg, float *exp_avg_sq, size_t offset, size_t n, const float *opt_state,
+                                  float beta1, float beta2, float eps, int rank, int world, int flag_slot, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,9 @@ SIGNATURES = {
     "vcm_adam_step_graph": (_i, [_p, _p, _p, _p, _sz, _p, _f, _f, _f, _f, _p]),
     "vcm_adam_advance": (_i, [_p, _f, _f, _p]),
     "vcm_adam_apply": (_i, [_p, _p, _p, _p, _sz, _p, _f, _f, _f, _f, _p]),
+    "vcm_reduce_adam_chunk": (_i, []),
+    "vcm_reduce_adam_blocks": (_i, [_sz, _i]),
+    "vcm_reduce_adam_bcast": (_i, [_p, _p, _p, _p, _p, _sz, _sz, _p, _f, _f, _f, _i, _i, _i, _p]),
     "vcm_reparam_kl_workspace": (_sz, [_sz]),
     "vcm_reparam_kl_fwd": (_i, [_p, _p, _p, _p, _p, _p, _sz, _f, _f, _p]),
     "vcm_reparam_kl_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _f, _f, _p]),

@@ -25,7 +25,7 @@
 namespace vcm {
 namespace {
 
-constexpr int kW = 4;              // warps per CTA
+constexpr int kW = 4;              // warps per CTA (independent: one vertex each)
 
 struct K1Params {
     const int32_t *idx_sorted;
@@ -82,118 +82,106 @@ __device__ __forceinline__ void x_rounds(uint32_t dst, const char *xb, const uin
     }
 }
 
-// NK = 8-neighbour k-steps (vertices of this launch have at most 8*NK neighbours), CW = columns per unit, MT = 16-row
-// basis tiles (1: M <= 16, 2: M <= 24 -- rows 24..31 of the second tile do not exist and are never stored)
+// One WARP = one output vertex x a share of its units: the warp loads the vertex's coefficient fragments straight
+// into registers, stages and multiplies its units, and never meets the other warps of the CTA (no __syncthreads: the
+// prologue of one warp - two dependent global loads - hides behind the main loops of the others).
+// NK = 8-neighbour k-steps the table width needs (<= 3: coefficient fragments live in registers), CW = columns per
+// unit, MT = 16-row basis tiles (1: M <= 16, 2: M <= 24 -- rows 24..31 of the second tile do not exist).
 template <int NK, int CW, int MT>
-__global__ void __launch_bounds__(32 * kW, NK <= 2 ? 4 : 2)
+__global__ void __launch_bounds__(32 * kW, 4)
 gather_fwd_tile_kernel(const K1Params P) {
     constexpr int NP = NK * 8;
     constexpr int RSB = (CW + 4) * 4;             // x row stride in bytes
-    constexpr int PIECES = CW / 4, RPR = 32 / PIECES, XR = NP / RPR, XK = XR < 8 ? XR : 8;
-    constexpr int ATS = NP + 4;                   // coefficient tile row stride (words): conflict-free ldmatrix
-    constexpr bool KEEP = NK <= 2;
+    constexpr int PIECES = CW / 4, RPR = 32 / PIECES, XK = NP / RPR;
     constexpr int STAGE = NP * RSB;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3, lr = lane & 7, lj = lane >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
     const int S = P.stages, M = P.M, I = P.I;
-    float *AT_s = reinterpret_cast<float *>(smem_raw + (size_t)kW * S * STAGE);   // [MT*16][ATS], k slots permuted
-    int32_t *idx_s = reinterpret_cast<int32_t *>(AT_s + MT * 16 * ATS);            // [NP]
-    float *raw_s = reinterpret_cast<float *>(idx_s + NP);                          // [l][M] as stored
     const uint32_t my_ring = smem_u32(smem_raw) + (uint32_t)(warp * S) * STAGE;
+    uint8_t *my_ring_p = smem_raw + (size_t)(warp * S) * STAGE;
 
-    const int slot = blockIdx.x + P.slot0;
+    const int slot = blockIdx.x * kW + warp;
+    if (slot >= P.p_out) return;
     const int2 meta = __ldg(P.meta_sorted + slot);
     const int p = meta.x, l = meta.y;
     const int total_units = P.B << P.cpi_shift, cpi_mask = (1 << P.cpi_shift) - 1;
     const int u_begin = blockIdx.y * P.units_per_cta;
     const int u_end = min(total_units, u_begin + P.units_per_cta);
+    const int32_t *idx_row = P.idx_sorted + (size_t)slot * P.n_max;
 
-    for (int n = tid; n < NP; n += blockDim.x) {
-        const int q = n < l ? __ldg(P.idx_sorted + (size_t)slot * P.n_max + n) : P.p_in;
-        idx_s[n] = q == P.p_in ? -1 : q;
-    }
-    {
-        const float *Ap = P.A + (size_t)p * P.n_max * M;
-        for (int e = tid; e < l * M; e += blockDim.x) raw_s[e] = __ldg(Ap + e);
-    }
-    __syncthreads();
-
-    // rows of the ring that no copy will ever write (padding neighbours) must be finite: zero them once
-    for (int s = 0; s < S; ++s)
-        for (int e = lane; e < NP * PIECES; e += 32) {
-            const int n = e / PIECES, j = e - n * PIECES;
-            if (idx_s[n] < 0)
-                *reinterpret_cast<float4 *>(smem_raw + (size_t)(warp * S + s) * STAGE + n * RSB + j * 16) =
-                    make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-
-    // x rows of a unit: round k of the warp covers rows k*RPR .. k*RPR+RPR-1, lane -> (row, 16-byte piece)
+    // x rows of a unit: round k of the warp covers rows k*RPR .. k*RPR+RPR-1, lane -> (row, 16-byte piece); byte
+    // offsets q * row_bytes of this lane's rows in registers (0xFFFFFFFF = no such neighbour: the row is zeroed once)
     const int xr0 = lane / PIECES, xj = lane % PIECES;
     const uint32_t x_dst0 = (uint32_t)(xr0 * RSB + xj * 16);
     const uint32_t row_bytes = (uint32_t)I * 4u;                     // q * row_bytes < 2^32 (checked by the plan)
     uint32_t xq[XK];
 #pragma unroll
     for (int k = 0; k < XK; ++k) {
-        const int q = idx_s[k * RPR + xr0];
-        xq[k] = q >= 0 ? (uint32_t)q * row_bytes : 0xFFFFFFFFu;
+        const int n = k * RPR + xr0;
+        const int q = n < l ? __ldg(idx_row + n) : P.p_in;
+        xq[k] = q != P.p_in ? (uint32_t)q * row_bytes : 0xFFFFFFFFu;
     }
+    // coefficient fragments AT[m][slot] of operand A, k slots permuted (slot t <-> neighbour 2t, slot t+4 <-> 2t+1):
+    // a0 = (m, 2t), a1 = (m+8, 2t), a2 = (m, 2t+1), a3 = (m+8, 2t+1), m = mt*16 + g; zero where basis or neighbour
+    // does not exist
+    uint32_t cT[MT][NK][4];
+    {
+        const float *Ap = P.A + (size_t)p * P.n_max * M;
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            const int n0 = ks * 8 + 2 * t, n1 = n0 + 1;
+            const bool v0 = n0 < l && __ldg(idx_row + min(n0, P.n_max - 1)) != P.p_in;
+            const bool v1 = n1 < l && __ldg(idx_row + min(n1, P.n_max - 1)) != P.p_in;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int m0 = mt * 16 + g, m1 = m0 + 8;
+                cT[mt][ks][0] = (v0 && m0 < M) ? __float_as_uint(__ldg(Ap + (size_t)n0 * M + m0)) : 0u;
+                cT[mt][ks][1] = (v0 && m1 < M) ? __float_as_uint(__ldg(Ap + (size_t)n0 * M + m1)) : 0u;
+                cT[mt][ks][2] = (v1 && m0 < M) ? __float_as_uint(__ldg(Ap + (size_t)n1 * M + m0)) : 0u;
+                cT[mt][ks][3] = (v1 && m1 < M) ? __float_as_uint(__ldg(Ap + (size_t)n1 * M + m1)) : 0u;
+            }
+        }
+    }
+    // rows of the ring that no copy will ever write (padding neighbours) must be finite: zero them once
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int k = 0; k < XK; ++k)
+            if (xq[k] == 0xFFFFFFFFu)
+                *reinterpret_cast<float4 *>(my_ring_p + (size_t)s * STAGE + x_dst0 + k * RPR * RSB) = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int nrounds = (l + RPR - 1) / RPR;                          // warp-uniform
     auto issue = [&](int u, int s) {
         const int b = u >> P.cpi_shift, ch = u & cpi_mask;
         const char *xb = reinterpret_cast<const char *>(P.x + (size_t)b * P.p_in * I + ch * CW + xj * 4);
         asm volatile("" : "+l"(xb));                                 // one 64-bit base per unit, not one per piece
         const uint32_t dst = my_ring + (uint32_t)s * STAGE + x_dst0;
-        if (XK <= 2 || l > 2 * RPR) {                                // warp-uniform
+        if (XK <= 2 || nrounds > 2) {
             x_rounds<0, XK, RPR * RSB, XK>(dst, xb, xq);
         } else {
             x_rounds<0, (XK < 2 ? XK : 2), RPR * RSB, XK>(dst, xb, xq);
         }
-        for (int k = XK; k * RPR < l; ++k) {                         // more than 8 rounds: the pooling layers
-            const int q = idx_s[k * RPR + xr0];
-            if (q >= 0) {
-                const char *src = xb + (uint32_t)q * row_bytes;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(k * RPR * RSB)), "l"(src) : "memory");
-            }
-        }
     };
-    int u = u_begin + warp;                                          // unit being multiplied
+    int u = u_begin;                                                 // unit being multiplied
     int u_issue = u;                                                 // next unit to request
     __syncwarp();
-    for (int s = 0; s < S - 1; ++s, u_issue += kW) {
+    for (int s = 0; s < S - 1; ++s, ++u_issue) {
         if (u_issue < u_end) issue(u_issue, s);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-    // coefficient tile AT[m][slot]: slot j of group ks <-> neighbour ks*8 + (j < 4 ? 2j : 2(j-4)+1); zero where the
-    // basis or the neighbour does not exist
-    for (int e = tid; e < MT * 16 * NP; e += blockDim.x) {
-        const int m = e / NP, c = e - m * NP, j = c & 7;
-        const int n = (c & ~7) + (j < 4 ? 2 * j : 2 * (j - 4) + 1);
-        AT_s[m * ATS + c] = (m < M && n < l && idx_s[n] >= 0) ? raw_s[n * M + m] : 0.f;
-    }
-    __syncthreads();
-
-    const uint32_t AT_u = smem_u32(AT_s);
-    const uint32_t c_row_off = (uint32_t)(((lj & 1) * 8 + lr) * ATS + (lj >> 1) * 4) * 4u;
-    uint32_t cT[KEEP ? MT : 1][KEEP ? NK : 1][4];
-    if (KEEP) {
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int ks = 0; ks < NK; ++ks) ldsm4(cT[mt][ks], AT_u + c_row_off + (uint32_t)(mt * 16 * ATS + ks * 8) * 4u);
-    }
     const int nks = (l + 7) >> 3;                                    // k-steps this vertex needs (warp-uniform)
     const uint32_t b_lane = (uint32_t)(2 * t * RSB + g * 4);         // row 2t, column g of a stage
     const bool st1 = MT > 1 && 16 + g < M;                           // this lane stores a row of the second tile
     const bool st0b = g + 8 < M, st0a = g < M;
 
     int stage = 0, fill = S - 1;                                     // stage being multiplied / refilled next
-    for (; u < u_end; u += kW) {
+    for (; u < u_end; ++u) {
         cp_wait_all_but(S - 2);                        // the oldest of the S - 1 groups in flight = this unit
         __syncwarp();
         if (u_issue < u_end) issue(u_issue, fill);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        u_issue += kW;
+        ++u_issue;
         if (++fill == S) fill = 0;
 
         const uint32_t xb = my_ring + (uint32_t)stage * STAGE + b_lane;
@@ -210,26 +198,13 @@ gather_fwd_tile_kernel(const K1Params P) {
             for (int ks = 0; ks < NK; ++ks) {
                 if (NK > 1 && ks >= nks) break;                      // warp-uniform
                 uint32_t b0, b1;
-                switch (ks) {                                        // immediates: ks * 8 rows, the odd row, the column block
+                switch (ks) {                                        // immediates: ks * 8 rows and the odd row
                     case 0: b0 = lds32_o<0 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<0 * 8 * RSB + RSB>(xb + c8 * 32); break;
                     case 1: b0 = lds32_o<1 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<1 * 8 * RSB + RSB>(xb + c8 * 32); break;
-                    case 2: b0 = lds32_o<2 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<2 * 8 * RSB + RSB>(xb + c8 * 32); break;
-                    case 3: b0 = lds32_o<3 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<3 * 8 * RSB + RSB>(xb + c8 * 32); break;
-                    case 4: b0 = lds32_o<4 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<4 * 8 * RSB + RSB>(xb + c8 * 32); break;
-                    case 5: b0 = lds32_o<5 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<5 * 8 * RSB + RSB>(xb + c8 * 32); break;
-                    case 6: b0 = lds32_o<6 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<6 * 8 * RSB + RSB>(xb + c8 * 32); break;
-                    default: b0 = lds32_o<7 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<7 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    default: b0 = lds32_o<2 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<2 * 8 * RSB + RSB>(xb + c8 * 32); break;
                 }
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    if (KEEP) {
-                        mma_tf32(d[mt], cT[mt][ks], b0, b1);
-                    } else {
-                        uint32_t a[4];
-                        ldsm4(a, AT_u + c_row_off + (uint32_t)(mt * 16 * ATS + ks * 8) * 4u);
-                        mma_tf32(d[mt], a, b0, b1);
-                    }
-                }
+                for (int mt = 0; mt < MT; ++mt) mma_tf32(d[mt], cT[mt][ks], b0, b1);
             }
             if (st0a) *reinterpret_cast<float2 *>(zp + c8 * 8) = make_float2(d[0][0], d[0][1]);
             if (st0b) *reinterpret_cast<float2 *>(zp8 + c8 * 8) = make_float2(d[0][2], d[0][3]);
@@ -240,43 +215,30 @@ gather_fwd_tile_kernel(const K1Params P) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-size_t cta_smem(int nk, int cw, int mt, int stages, int M) {
-    const int np = nk * 8;
-    return (size_t)kW * stages * np * (cw + 4) * 4 + (size_t)mt * 16 * (np + 4) * 4 + (size_t)np * 4 + (size_t)np * M * 4 + 16;
-}
+size_t cta_smem(int nk, int cw, int stages) { return (size_t)kW * stages * nk * 8 * (cw + 4) * 4; }
 
 template <int NK, int CW, int MT>
-int launch_bucket(const Tables *t, const K1TilePlan &pl, K1Params P, int n_slots, cudaStream_t st) {
-    if (n_slots <= 0) return VCM_OK;
-    int stages = pl.stages;
-    while (stages > 2 && cta_smem(NK, CW, MT, stages, P.M) > 56 * 1024) --stages;
-    P.stages = stages;
-    const size_t smem = cta_smem(NK, CW, MT, stages, P.M);
+int launch_tile(const Tables *t, const K1TilePlan &pl, K1Params P, cudaStream_t st) {
+    const size_t smem = cta_smem(NK, CW, pl.stages);
     auto k = gather_fwd_tile_kernel<NK, CW, MT>;
     static size_t configured = 0;
     if (smem > configured) {
         VCM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid((unsigned)n_slots, (unsigned)pl.gy);
+    dim3 grid((unsigned)ceil_div(t->p_out, kW), (unsigned)pl.gy);
     k<<<grid, 32 * kW, smem, st>>>(P);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
 
-// Degree buckets of the processing order (vertices sorted by neighbour count, descending): slots [0, n_gt16) run the
-// kernel sized for the table width, the rest the 16-neighbour kernel.
 template <int CW, int MT>
 int launch_all(const Tables *t, const K1TilePlan &pl, K1Params P, cudaStream_t st) {
-    const int n_hi = pl.nk > 2 ? t->n_gt16 : 0;
-    int e = VCM_OK;
-    P.slot0 = 0;
-    if (pl.nk > 4) e = launch_bucket<8, CW, MT>(t, pl, P, n_hi, st);
-    else if (pl.nk > 2) e = launch_bucket<4, CW, MT>(t, pl, P, n_hi, st);
-    if (e) return e;
-    P.slot0 = n_hi;
-    if (pl.nk == 1) return launch_bucket<1, CW, MT>(t, pl, P, t->p_out - n_hi, st);
-    return launch_bucket<2, CW, MT>(t, pl, P, t->p_out - n_hi, st);
+    switch (pl.nk) {
+        case 1: return launch_tile<1, CW, MT>(t, pl, P, st);
+        case 2: return launch_tile<2, CW, MT>(t, pl, P, st);
+        default: return launch_tile<3, CW, MT>(t, pl, P, st);
+    }
 }
 
 }  // namespace
@@ -289,17 +251,19 @@ bool k1_tile_plan(const Tables *t, int B, int I, int M, int precision, K1TilePla
     if ((cpi32 & (cpi32 - 1)) != 0) return false;
     if ((int64_t)t->p_in * I * 4 >= (int64_t)1 << 32) return false;
     pl->nk = (t->n_max + 7) / 8;
+    if (pl->nk > 3) return false;                                    // the pooling layers keep the fp32 kernel
     pl->cw = (I % 64 == 0) ? tune_flag("VCM_K1_CW", 32) : 32;
     if (pl->cw != 32 && pl->cw != 64) pl->cw = 32;
     pl->stages = tune_flag("VCM_K1_STAGES", 3);
     if (pl->stages < 2) pl->stages = 2;
     if (pl->stages > 8) pl->stages = 8;
     const int units = B * (I / pl->cw);
-    int64_t want = ceil_div((int64_t)tune_flag("VCM_K1_CTAS_PER_SM", 8) * sm_count(), t->p_out);
-    const int64_t max_gy = ceil_div(units, (int64_t)kW * 4);
+    // one warp per (vertex, share of its units): enough warps to fill the machine, at least 4 units each
+    int64_t want = ceil_div((int64_t)tune_flag("VCM_K1_WARPS_PER_SM", 32) * sm_count(), t->p_out);
+    const int64_t max_gy = ceil_div(units, 4);
     if (want > max_gy) want = max_gy;
     if (want < 1) want = 1;
-    pl->units_per_cta = (int)(ceil_div(ceil_div(units, want), kW) * kW);
+    pl->units_per_cta = (int)ceil_div(units, want);
     pl->gy = (int)ceil_div(units, pl->units_per_cta);
     return true;
 }

@@ -12,6 +12,7 @@
 // W is consumed in the reference's native parameter layout [M][O][I]
 // (`weights.view(M, O, I)`, graphVAESSW.py:125): element (k = m*I + i, o) lives
 // at (m*O + o)*I + i, so no transposed copy of the bases is ever made.
+#include "adam.cuh"
 #include "gemm.h"
 
 namespace vcm {
@@ -469,15 +470,6 @@ __global__ void adam_advance_kernel(float *state, float b1, float b2) {
     state[0] = t;
     state[2] = 1.f - powf(b1, t);
     state[3] = sqrtf(1.f - powf(b2, t));
-}
-__device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, float b1, float b2, float eps,
-                                         float step_size, float bc2_sqrt, float grad_scale) {
-    const float gi = g * grad_scale;
-    const float mi = b1 * m + (1.f - b1) * gi;
-    const float vi = b2 * v + (1.f - b2) * gi * gi;
-    m = mi;
-    v = vi;
-    p -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
 }
 // 16-byte accesses over the aligned body (four streams of 128-bit loads in flight per thread), scalar tail.
 __global__ void adam_dev_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,

@@ -153,9 +153,9 @@ class FlatBuffers:
     fp32 buffers. Layout follows backward order (decoder last layer first) so a
     bucket is a contiguous slice that becomes ready as a whole."""
 
-    def __init__(self, params, bucket_bytes=32 << 20, grad_alloc=None):
-        """`grad_alloc(n)` may supply the gradient buffer (e.g. a symmetric-memory allocation that peer GPUs can
-        address); default torch.zeros."""
+    def __init__(self, params, bucket_bytes=32 << 20, grad_alloc=None, param_alloc=None):
+        """`grad_alloc(n)` / `param_alloc(n)` may supply the gradient / parameter buffer (e.g. symmetric-memory
+        allocations that peer GPUs can address); default torch.zeros."""
         params = list(params)
         dev = params[0].device
         # autograd reaches parameters roughly in reverse creation order of use; bucket order only
@@ -168,7 +168,8 @@ class FlatBuffers:
             offs.append(total)
             total += pad(n)
         self.total = total
-        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_p = (param_alloc(total).zero_() if param_alloc is not None else
+                       torch.zeros(total, device=dev, dtype=torch.float32))
         self.flat_g = grad_alloc(total).zero_() if grad_alloc is not None else torch.zeros(total, device=dev,
                                                                                             dtype=torch.float32)
         self.offsets = offs
@@ -213,14 +214,16 @@ class DataParallelTrainer:
         ordered = [p for seg in segs for p in seg]
         self._symm_op, grad_alloc = self._symmetric_allreduce(ordered)
         try:
-            self.flat = FlatBuffers(ordered, bucket_bytes, grad_alloc)
+            self.flat = FlatBuffers(ordered, bucket_bytes, grad_alloc, grad_alloc if self._symm_op == "fused" else None)
             if self._symm_op is not None:
-                self._symm_mem.rendezvous(self.flat.flat_g, self._symm_group)
+                hg = self._symm_mem.rendezvous(self.flat.flat_g, self._symm_group)
+                if self._symm_op == "fused":
+                    self._setup_fused(hg)
         except Exception as e:                   # no symmetric memory on this system: NCCL between two graphs
             if grad_alloc is None:
                 raise
             import sys
-            sys.stderr.write("vcmeshconv_b200: symmetric-memory all-reduce unavailable (%r), using NCCL\n" % (e,))
+            sys.stderr.write("vcmeshconv_b200: symmetric-memory reduction unavailable (%r), using NCCL\n" % (e,))
             self._symm_op = None
             self.flat = FlatBuffers(ordered, bucket_bytes)
         # early_bounds[i] = end of segment i in the flat buffers; the last segment is never "early"
@@ -254,7 +257,8 @@ class DataParallelTrainer:
                              if self.flat.flat_p.is_cuda and os.environ.get("VCM_EARLY_UPDATE", "1") == "1" else None)
         self._advanced = self._early_done = False
         self._early_upto = 0
-        self.overlap = overlap and self.world > 1
+        self.overlap = overlap and self.world > 1 and self._symm_op != "fused"
+        self._seg = 0                                # which range of the step the next fused reduction covers
         self._pending = []
         self._handles = []
         if self.overlap:
@@ -272,20 +276,54 @@ class DataParallelTrainer:
         of the backward pass and the whole multi-GPU step is ONE graph launch (8 x B200: 2.62 vs 2.80 ms/step with
         NCCL between two graphs). Returns (op name or None, allocator or None); the caller falls back to NCCL when
         the allocation is not available."""
-        mode = os.environ.get("VCM_SYMM_AR", "two_shot")
+        mode = os.environ.get("VCM_SYMM_AR", "fused")
         if mode in ("0", "") or self.world == 1 or not params or not params[0].is_cuda:
             return None, None
+        if self.world > 8 and mode == "fused":
+            mode = "two_shot"
         import torch.distributed._symmetric_memory as symm_mem
-        op = {"two_shot": "two_shot_all_reduce_", "multimem": "multimem_all_reduce_"}[mode]
+        op = {"fused": "fused", "two_shot": "two_shot_all_reduce_", "multimem": "multimem_all_reduce_"}[mode]
         self._symm_mem = symm_mem
         self._symm_group = (self.group if self.group is not None else dist.group.WORLD).group_name
         dev = params[0].device
         return op, (lambda n: symm_mem.empty(n, dtype=torch.float32, device=dev))
 
+    def _setup_fused(self, hg):
+        """VCM_SYMM_AR=fused (the multi-GPU default): the repo's own reduce + Adam + broadcast kernel
+        (csrc/collective.cu, vcm_reduce_adam_bcast) over the peers' gradient, parameter and flag buffers, all three
+        in symmetric memory. Collects every rank's base pointers as this process maps them."""
+        import ctypes as C
+        dev = self.flat.flat_p.device
+        hp = self._symm_mem.rendezvous(self.flat.flat_p, self._symm_group)
+        self._flags = self._symm_mem.empty(8 * 3 * 128, dtype=torch.int32, device=dev).zero_()
+        hf = self._symm_mem.rendezvous(self._flags, self._symm_group)
+        arr = C.c_void_p * self.world
+
+        def peers(h, tensor):
+            ptrs = [int(h.buffer_ptrs[k]) + (int(tensor.data_ptr()) - int(h.buffer_ptrs[self.rank])) for k in range(self.world)]
+            return arr(*ptrs)
+        self._peer_g, self._peer_p, self._peer_f = peers(hg, self.flat.flat_g), peers(hp, self.flat.flat_p), peers(hf, self._flags)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)               # every rank's flags are zero before anyone signals
+
+    def _reduce_update(self, lo, hi):
+        """Fused path: SUM over ranks of flat_g[lo:hi] -> Adam on the chunks this rank owns -> new parameters into
+        every rank's flat_p. One launch; every rank issues the same ranges in the same order."""
+        if hi <= lo:
+            return
+        f = self.flat
+        _lib.call("vcm_reduce_adam_bcast", self._peer_g, self._peer_p, self._peer_f, self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), lo, hi - lo, self.opt_state.data_ptr(), self.betas[0], self.betas[1],
+                  self.eps, self.rank, self.world, 128 * (self._seg % 3), _lib.stream_ptr(),
+                  nbytes=4 * (hi - lo) * (2 * self.world + 5) // self.world, flops=12 * (hi - lo) // self.world)
+        self._seg += 1
+
     def _allreduce(self, lo, hi):
         """SUM over ranks of flat_g[lo:hi], in place, on the current stream."""
         if hi <= lo:
             return
+        if self._symm_op == "fused":
+            raise RuntimeError("the fused path reduces inside _reduce_update")
         if self._symm_op is not None:
             getattr(torch.ops.symm_mem, self._symm_op)(self.flat.flat_g[lo:hi], "sum", self._symm_group)
         else:
@@ -353,7 +391,7 @@ class DataParallelTrainer:
             for h in self._handles:
                 h.wait()
             self._handles = []
-        else:
+        elif self._symm_op != "fused":                              # fused: optimizer_step reduces what is left
             self._allreduce(self._early_upto, self.flat.total)      # [0, _early_upto) was reduced next to the backward pass
 
     # -- one training step ---------------------------------------------------------
@@ -430,9 +468,12 @@ class DataParallelTrainer:
                         continue
             s.wait_stream(st)
         with torch.cuda.stream(s):
-            if self.world > 1:
-                self._allreduce(lo, hi)
-            self._apply(lo, hi)
+            if self.world > 1 and self._symm_op == "fused":
+                self._reduce_update(lo, hi)
+            else:
+                if self.world > 1:
+                    self._allreduce(lo, hi)
+                self._apply(lo, hi)
         self._early_upto = hi
         self._early_done = True
 
@@ -464,9 +505,13 @@ class DataParallelTrainer:
             raise RuntimeError("the optimizer step runs on CUDA only (no CPU fallback)")
         if not self._advanced:
             self._advance()
-        self._apply(self._early_upto, f.total)
+        if self.world > 1 and self._symm_op == "fused":
+            self._reduce_update(self._early_upto, f.total)
+        else:
+            self._apply(self._early_upto, f.total)
         self._advanced = self._early_done = False
         self._early_upto = 0
+        self._seg = 0
 
     def step(self, pc, nor, eps=None):
         if self._graph is not None and (eps is None or self.static_eps is not None):
@@ -592,6 +637,29 @@ class DataParallelTrainer:
         return self.static_loss, self.static_parts
 
     # -- checkpoint layout of the reference (graphVAE_train.py:339-347) ----------
+    def _sharded_moments(self):
+        return self.world > 1 and self._symm_op == "fused"
+
+    def _full_moments(self):
+        """The Adam moments over the whole flat buffer. On the fused multi-GPU path each rank keeps them for the
+        chunks it owns only (zero elsewhere): summing over the ranks assembles them. Collective in that case."""
+        if not self._sharded_moments():
+            return self.exp_avg, self.exp_avg_sq
+        m, v = self.exp_avg.clone(), self.exp_avg_sq.clone()
+        dist.all_reduce(m, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+        return m, v
+
+    def _keep_owned_moments(self):
+        """After loading full moments on the fused path: zero what this rank does not own (chunk c of the flat buffer
+        belongs to rank c % world, include/vcmesh.h vcm_reduce_adam_bcast), so that _full_moments stays a plain sum."""
+        if not self._sharded_moments():
+            return
+        chunk = _lib.lib().vcm_reduce_adam_chunk()
+        own = (torch.arange(self.flat.total, device=self.exp_avg.device) // chunk) % self.world == self.rank
+        self.exp_avg.mul_(own)
+        self.exp_avg_sq.mul_(own)
+
     def optimizer_state_dict(self):
         """The Adam state exactly as `torch.optim.Adam.state_dict()` lays it out for the reference's optimizer
         (graphVAE_train.py:252-262, 280, 345): `state[i]` = {step, exp_avg, exp_avg_sq} of the i-th parameter in
@@ -599,14 +667,15 @@ class DataParallelTrainer:
         moment buffers are sliced per parameter, so the reference's `optimizer.load_state_dict(...)` (:291) accepts
         the file and resumes with the right bias correction."""
         step = float(self.step_count)
+        exp_avg, exp_avg_sq = self._full_moments()
         by_id = {id(p): (o, p) for p, o in zip(self.flat.params, self.flat.offsets)}
         state, order = {}, self.model.trainable_parameters()
         for i, p in enumerate(order):
             o, _ = by_id[id(p)]
             n = p.numel()
             state[i] = {"step": torch.tensor(step, dtype=torch.float32),
-                        "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
-                        "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+                        "exp_avg": exp_avg[o:o + n].view(p.shape).clone(),
+                        "exp_avg_sq": exp_avg_sq[o:o + n].view(p.shape).clone()}
         group = {"lr": float(self.lr), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0,
                  "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
                  "differentiable": False, "fused": None, "decoupled_weight_decay": False,
@@ -652,6 +721,7 @@ class DataParallelTrainer:
                 self.set_lr(float(opt.get("lr", self.lr)))
             else:
                 raise RuntimeError("unknown optimizer_state_dict layout: keys %s" % sorted(opt))
+            self._keep_owned_moments()
 
     def state_dict(self):
         m = self.model
@@ -662,9 +732,11 @@ class DataParallelTrainer:
     def save(self, folder, iteration):
         """Writes `model_%07d_best.weight` exactly as the reference does (graphVAE_train.py:341-347), optimizer
         state included in torch.optim.Adam's own layout."""
-        os.makedirs(folder, exist_ok=True)
         path = os.path.join(folder, "model_%07d" % iteration + "_best.weight")
-        torch.save(self.state_dict(), path)
+        sd = self.state_dict()                       # every rank takes part (the fused path shards the Adam moments)
+        if self.rank == 0:
+            os.makedirs(folder, exist_ok=True)
+            torch.save(sd, path)
         return path
 
     def load(self, path):
@@ -688,8 +760,8 @@ class DataParallelTrainer:
                 loss, parts = self.step(pc, nor)
                 if log is not None:
                     log(iteration, loss, parts)
-                if every and iteration % every == 0 and self.rank == 0:
-                    self.save(param.write_weight_folder, iteration)
+                if every and iteration % every == 0:
+                    self.save(param.write_weight_folder, iteration)      # collective; rank 0 writes the file
                 iteration += 1
                 if iteration > end_iter:
                     break
