@@ -655,7 +655,17 @@ def roofline(runner, steps, dump=""):
             torch.cuda._sleep(delay)
             runner.step(i)
             torch.cuda.synchronize()
-    summ = prof.summary()
+    # what an event pair around nothing measures behind the same delay (the two record commands): subtracted per call
+    torch.cuda._sleep(delay)
+    pairs = []
+    for _ in range(200):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); b.record()
+        pairs.append((a, b))
+    torch.cuda.synchronize()
+    empty = sorted(a.elapsed_time(b) for a, b in pairs)
+    pair_ms = empty[len(empty) // 2]
+    summ = prof.summary(pair_ms)
     total = sum(v["ms"] for v in summ.values())
     if dump:
         with open(dump, "w") as f:
@@ -711,10 +721,12 @@ def roofline(runner, steps, dump=""):
             "algorithmic_bytes_per_launch": g["bytes"] / g["calls"], "share_of_step": g["ms"] / total,
             "shapes": shapes[:4], "ranking": ranking,
             "whole_step": {"algorithmic_bytes": sum(v["bytes"] for v in summ.values()) / steps,
-                           "sum_of_kernel_ms": total / steps},
+                           "sum_of_kernel_ms": total / steps, "calls_per_step": sum(v["calls"] for v in summ.values()) / steps,
+                           "event_pair_overhead_us_subtracted_per_call": 1e3 * pair_ms},
             "how": "CUDA events on the launching stream around every C-ABI call of %d eager one-stream steps run right "
                    "after the timed region, each step queued behind a ~20 ms device-side delay so that no host launch "
-                   "gap falls inside an event pair; all launches of the kernel (%d layer shapes) summed; the dominant "
+                   "gap falls inside an event pair (the median time of an empty event pair is subtracted per call); all launches "
+                   "of the kernel (%d layer shapes) summed; the dominant "
                    "kernel is the (entry point, kernel variant) with the largest summed device time" % (steps, len(shapes))}
     return roof, breakdown
 

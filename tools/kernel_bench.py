@@ -87,8 +87,8 @@ def main():
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
     ms = tot / a.iters
-    print("%s %s  P %d->%d N %d nnz %d I %d O %d B %d : %.1f us  %.0f GB/s (algorithmic)  %.2f TFLOP/s" %
-          (a.layer, a.kernel, p_in, P, N, nnz, I, O, B, ms * 1e3, nbytes / ms / 1e6, flops / ms / 1e9))
+    print("%s %s  P %d->%d N %d nnz %d I %d O %d B %d : %.1f us  %.0f GB/s (algorithmic)  %.2f TFLOP/s  bytes=%d" %
+          (a.layer, a.kernel, p_in, P, N, nnz, I, O, B, ms * 1e3, nbytes / ms / 1e6, flops / ms / 1e9, nbytes))
 
 
 if __name__ == "__main__":

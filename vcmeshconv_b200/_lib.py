@@ -123,13 +123,15 @@ class Profiler:
         global _profiler
         _profiler = None
 
-    def summary(self):
+    def summary(self, pair_overhead_ms=0.0):
+        """`pair_overhead_ms`: what an event pair around NOTHING measures on this stream (the record commands
+        themselves); it is subtracted from every call's time."""
         import torch
         torch.cuda.synchronize()
         out = {}
         for name, tag, nbytes, flops, e0, e1 in self.records:
             d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0, "by_tag": {}})
-            ms = e0.elapsed_time(e1)
+            ms = max(e0.elapsed_time(e1) - pair_overhead_ms, 1e-4)
             d["calls"] += 1
             d["ms"] += ms
             d["bytes"] += nbytes

@@ -15,11 +15,11 @@
 //   dA[n][m] += X[n][c] dz[m][c]^T  mma.sync m16n8k8 tf32: M = neighbours, N = bases, K = columns; both operands are
 //                                   k-contiguous, every fragment is one ldmatrix; accumulates in fragments over all
 //                                   units of the warp, fixed-order sum over warps (and CTAs) at the end: no atomics;
-//   dG[n][c]  = A_p[n][m] dz[m][c]  M = neighbours, N = columns, K = bases. The coefficient tile is built in shared
-//                                   memory with its k slots PERMUTED (slot j of an 8-group holds basis 2j, slot j+4
-//                                   basis 2j+1): the order of k is free as long as both operands agree, and with this
-//                                   one the scalar transposed dz fragment loads (lane (g,t): bases 2t, 2t+1, column g)
-//                                   touch 32 different banks under TMA's 128-byte swizzle.
+//   dG[n][c]  = A_p[n][m] dz[m][c]  M = neighbours, N = columns, K = bases. dz is needed with k = basis, the transposed
+//                                   access; the MMA's n slots are PERMUTED (slot g of the j-th 8-column block is
+//                                   column c0(g) + j), so one 128-bit LDS per basis row feeds four MMA blocks, is
+//                                   bank-conflict-free under TMA's 128-byte swizzle, and the results leave as 128-bit
+//                                   stores that write whole sectors.
 // Rows that do not exist (bases >= M, padding neighbours) alias rows that do (see below): no predicates in the loop.
 // Against the cp.async-only kernel of gather.cu (per 32-column tile ~375 warp instructions, 170 of them staging) this
 // one spends ~25 on staging per 64-column unit.
@@ -72,6 +72,13 @@ template <int OFF>
 __device__ __forceinline__ void ldsm2_o(uint32_t &r0, uint32_t &r1, uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2+%3];" : "=r"(r0), "=r"(r1) : "r"(addr), "n"(OFF));
 }
+template <int OFF>
+__device__ __forceinline__ uint4 lds128_o(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ uint32_t comp(const uint4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
 template <int OFF>
 __device__ __forceinline__ uint32_t lds32_o(uint32_t addr) {
     uint32_t v;
@@ -226,12 +233,10 @@ coeff_grad_tma_kernel(const __grid_constant__ CUtensorMap map_dz, const K5Params
         for (int s = 0; s < n_pro; ++s, uu += W) issue_x(uu, s);
     }
 
-    // coefficient tile with permuted k slots (slot j of group ks <-> basis ks*8 + (j < 4 ? 2j : 2(j-4)+1)); rows and
-    // bases that do not exist are zero
+    // coefficient tile [neighbour][basis]; rows and bases that do not exist are zero
     for (int e = tid; e < NP * 24; e += blockDim.x) {
-        const int n = e / 24, c = e - n * 24, j = c & 7;
-        const int m = (c & ~7) + (j < 4 ? 2 * j : 2 * (j - 4) + 1);
-        A_s[n * kAS + c] = (n < l && m < M && idx_s[n] >= 0) ? raw_s[n * M + m] : 0.f;
+        const int n = e / 24, m = e - n * 24;
+        A_s[n * kAS + m] = (n < l && m < M && idx_s[n] >= 0) ? raw_s[n * M + m] : 0.f;
     }
     __syncthreads();
 
@@ -256,17 +261,25 @@ coeff_grad_tma_kernel(const __grid_constant__ CUtensorMap map_dz, const K5Params
             offB[blk] = (uint32_t)(r4 * 128 + ((((lj & 1) ^ r4) & 7) << 4));
         }
     }
-    // dz words of the scalar B fragments of dG: bases ks*8 + 2t + h (h = 0, 1), column c8*8 + g. ks adds 8 rows = 1024
-    // bytes and leaves the swizzle alone: one base per (h, block), the three k-steps are immediate offsets. Rows past
-    // the tile (bases >= M of the last block) fall into the head of the x area, which is kept finite (zeroed below).
+    // dz fragments of dG (operand B: k = basis, n = column). The order of the MMA's n slots is free: slot g of the j-th
+    // 8-column block stands for column c0(g) + j of a 32-column block, c0 = 0,16,4,20,8,24,12,28 for g = 0..7. ONE
+    // 128-bit load (row = basis ks*8 + t + 4h, 16-byte chunk c0(g)/4) then feeds four MMA blocks, and a lane's results
+    // are columns 4t..4t+3 (slot 2t) and 16+4t..16+4t+3 (slot 2t+1) of its two neighbour rows: two 128-bit stores per
+    // row, each instruction writing whole 32-byte sectors. ks adds 8 rows = 1024 bytes and leaves the swizzle alone
+    // (immediate offsets); a quarter warp (g in {0,1}, t = 0..3) touches the 8 different chunks {s_t, s_t ^ 4} of its
+    // four rows (s_t = (r0 + t) & 7). Rows past the tile (bases >= M of the last block) fall into the head of the x
+    // area, which is kept finite (zeroed above).
     uint32_t zoff[2][NBLK];
+    {
+        const int chunk = (g & 1) ? 4 + (g >> 1) : (g >> 1);
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) {
-            const int r = blk * M + 2 * t + h;
-            zoff[h][blk] = (uint32_t)(r * 128 + ((((g >> 2) ^ r) & 7) << 4) + ((g & 3) << 2));
-        }
+            for (int blk = 0; blk < NBLK; ++blk) {
+                const int r = blk * M + t + 4 * h;
+                zoff[h][blk] = (uint32_t)(r * 128 + (((chunk ^ r) & 7) << 4));
+            }
+    }
     // coefficient fragments (operand A of dG) and the dG rows this lane stores
     const uint32_t A_u = smem_u32(A_s);
     const uint32_t c_row_off = (uint32_t)(((lj & 1) * 8 + lr) * kAS + (lj >> 1) * 4) * 4u;
@@ -325,58 +338,42 @@ coeff_grad_tma_kernel(const __grid_constant__ CUtensorMap map_dz, const K5Params
         }
         if (HAS_DG) {
             const int b = u >> P.cpi_shift, ch = u & cpi_mask;
-            float *dGp = P.dG + (((size_t)b * P.p_out + p) * P.n_max + g) * I + ch * CW + 2 * t;
-            if (KEEP) {
+            float *dGp = P.dG + (((size_t)b * P.p_out + p) * P.n_max + g) * I + ch * CW + 4 * t;
 #pragma unroll
-                for (int c8 = 0; c8 < CW / 8; ++c8) {
-                    const int blk = c8 >> 2;
-                    const uint32_t cx = (uint32_t)(c8 & 3) << 5;
-                    uint32_t zb[6];
+            for (int blk = 0; blk < NBLK; ++blk) {
+                uint4 zb[3][2];                                      // [k-step][h]: basis ks*8 + t + 4h, columns c0(g)..c0(g)+3
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t az = aZ[h][blk] ^ cx;
-                        zb[h] = lds32_o<0>(az);
-                        zb[2 + h] = lds32_o<1024>(az);
-                        zb[4 + h] = lds32_o<2048>(az);
-                    }
-#pragma unroll
-                    for (int nt = 0; nt < NT16; ++nt) {
-                        if (NT16 > 1 && nt * 16 >= l) break;         // warp-uniform
-                        float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) mma_tf32(d, cA[nt][ks], zb[2 * ks], zb[2 * ks + 1]);
-                        float *row0 = dGp + (size_t)(nt * 16) * I + c8 * 8;
-                        if (st_mask & (1u << (2 * nt))) *reinterpret_cast<float2 *>(row0) = make_float2(d[0], d[1]);
-                        if (st_mask & (2u << (2 * nt))) *reinterpret_cast<float2 *>(row0 + (size_t)8 * I) = make_float2(d[2], d[3]);
-                    }
+                for (int h = 0; h < 2; ++h) {
+                    zb[0][h] = lds128_o<0>(aZ[h][blk]);
+                    zb[1][h] = lds128_o<1024>(aZ[h][blk]);
+                    zb[2][h] = lds128_o<2048>(aZ[h][blk]);
                 }
-            } else {
-                // many neighbours: the dz fragments of the whole unit stay in registers, the coefficient fragments
-                // of one 16-neighbour block are loaded once per unit
-                uint32_t zb[CW / 8][6];
-#pragma unroll
-                for (int c8 = 0; c8 < CW / 8; ++c8)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t az = aZ[h][c8 >> 2] ^ ((uint32_t)(c8 & 3) << 5);
-                        zb[c8][h] = lds32_o<0>(az);
-                        zb[c8][2 + h] = lds32_o<1024>(az);
-                        zb[c8][4 + h] = lds32_o<2048>(az);
-                    }
 #pragma unroll
                 for (int nt = 0; nt < NT16; ++nt) {
-                    if (nt * 16 >= l) break;                         // warp-uniform
+                    if (NT16 > 1 && nt * 16 >= l) break;             // warp-uniform
                     uint32_t ca[3][4];
+                    if (!KEEP) {
 #pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) ldsm4(ca[ks], A_u + c_row_off + (uint32_t)(nt * 16 * kAS + ks * 8) * 4u);
+                        for (int ks = 0; ks < 3; ++ks) ldsm4(ca[ks], A_u + c_row_off + (uint32_t)(nt * 16 * kAS + ks * 8) * 4u);
+                    }
+                    float d[4][4];
 #pragma unroll
-                    for (int c8 = 0; c8 < CW / 8; ++c8) {
-                        float d[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int j = 0; j < 4; ++j) {
+                        d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
 #pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) mma_tf32(d, ca[ks], zb[c8][2 * ks], zb[c8][2 * ks + 1]);
-                        float *row0 = dGp + (size_t)(nt * 16) * I + c8 * 8;
-                        if (st_mask & (1u << (2 * nt))) *reinterpret_cast<float2 *>(row0) = make_float2(d[0], d[1]);
-                        if (st_mask & (2u << (2 * nt))) *reinterpret_cast<float2 *>(row0 + (size_t)8 * I) = make_float2(d[2], d[3]);
+                        for (int ks = 0; ks < 3; ++ks)
+                            mma_tf32(d[j], KEEP ? cA[KEEP ? nt : 0][ks] : ca[ks], comp(zb[ks][0], j), comp(zb[ks][1], j));
+                    }
+                    // block j, fragment (c0, c1) = columns (4t + j, 16 + 4t + j) of row g; (c2, c3) the same of row g + 8
+                    float *row0 = dGp + (size_t)(nt * 16) * I + blk * 32;
+                    if (st_mask & (1u << (2 * nt))) {
+                        *reinterpret_cast<float4 *>(row0) = make_float4(d[0][0], d[1][0], d[2][0], d[3][0]);
+                        *reinterpret_cast<float4 *>(row0 + 16) = make_float4(d[0][1], d[1][1], d[2][1], d[3][1]);
+                    }
+                    if (st_mask & (2u << (2 * nt))) {
+                        float *row8 = row0 + (size_t)8 * I;
+                        *reinterpret_cast<float4 *>(row8) = make_float4(d[0][2], d[1][2], d[2][2], d[3][2]);
+                        *reinterpret_cast<float4 *>(row8 + 16) = make_float4(d[0][3], d[1][3], d[2][3], d[3][3]);
                     }
                 }
             }

@@ -13,9 +13,9 @@
 //
 // The coefficient fragments AT (per vertex, constant over its units) live in registers (<= 16 neighbours) or are
 // re-read from the shared tile once per unit. The x fragments need x[n][c] with k = n, i.e. the transposed access:
-// scalar LDS, made bank-conflict-free by PERMUTING the k slots (slot j of an 8-group holds neighbour 2j, slot j+4
-// neighbour 2j+1: lane (g,t) reads rows 2t, 2t+1, column g; with rows padded by 16 bytes the 32 lanes hit 32 banks);
-// every address is one per-unit base plus immediates. Results leave as 8-byte stores, 32 bytes per row segment.
+// the MMA's n slots are PERMUTED (slot g of the j-th 8-column block is column c0(g) + j, c0 = 0,16,4,20,8,24,12,28), so a
+// lane reads rows t, t+4 at four consecutive columns with one bank-conflict-free 128-bit LDS per row for FOUR MMA
+// blocks; every address is one per-unit base plus immediates. Results leave as 128-bit stores that write whole sectors.
 // Padding neighbours meet a zero coefficient and a zeroed row. Per 32-column unit of an 8-neighbour vertex: ~65 warp
 // instructions for 2176 bytes of z (the fp32 kernel: ~320 per 1088 bytes).
 #include "common.cuh"
@@ -47,11 +47,12 @@ __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 template <int OFF>
-__device__ __forceinline__ uint32_t lds32_o(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+__device__ __forceinline__ uint4 lds128_o(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
     return v;
 }
+__device__ __forceinline__ uint32_t comp(const uint4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
 // 16-byte cp.async, skipped when off == 0xFFFFFFFF (predicated inside the asm: no branch around it)
 template <int DOFF>
 __device__ __forceinline__ void cp16_if(uint32_t dst, const char *base, uint32_t off) {
@@ -122,15 +123,14 @@ gather_fwd_tile_kernel(const K1Params P) {
         const int q = n < l ? __ldg(idx_row + n) : P.p_in;
         xq[k] = q != P.p_in ? (uint32_t)q * row_bytes : 0xFFFFFFFFu;
     }
-    // coefficient fragments AT[m][slot] of operand A, k slots permuted (slot t <-> neighbour 2t, slot t+4 <-> 2t+1):
-    // a0 = (m, 2t), a1 = (m+8, 2t), a2 = (m, 2t+1), a3 = (m+8, 2t+1), m = mt*16 + g; zero where basis or neighbour
-    // does not exist
+    // coefficient fragments AT[m][n] of operand A: a0 = (m, t), a1 = (m+8, t), a2 = (m, t+4), a3 = (m+8, t+4) of
+    // k-step ks (neighbours ks*8 ..), m = mt*16 + g; zero where basis or neighbour does not exist
     uint32_t cT[MT][NK][4];
     {
         const float *Ap = P.A + (size_t)p * P.n_max * M;
 #pragma unroll
         for (int ks = 0; ks < NK; ++ks) {
-            const int n0 = ks * 8 + 2 * t, n1 = n0 + 1;
+            const int n0 = ks * 8 + t, n1 = n0 + 4;
             const bool v0 = n0 < l && __ldg(idx_row + min(n0, P.n_max - 1)) != P.p_in;
             const bool v1 = n1 < l && __ldg(idx_row + min(n1, P.n_max - 1)) != P.p_in;
 #pragma unroll
@@ -171,7 +171,12 @@ gather_fwd_tile_kernel(const K1Params P) {
     }
 
     const int nks = (l + 7) >> 3;                                    // k-steps this vertex needs (warp-uniform)
-    const uint32_t b_lane = (uint32_t)(2 * t * RSB + g * 4);         // row 2t, column g of a stage
+    // x fragments (operand B: k = neighbour, n = column). The order of the MMA's n slots is free: slot g of the j-th
+    // 8-column block stands for column c0(g) + j of a 32-column block, c0 = 0,16,4,20,8,24,12,28 for g = 0..7. ONE
+    // 128-bit load (row t + 4h, columns c0(g)..c0(g)+3) then feeds four MMA blocks, and a lane's results are columns
+    // 4t..4t+3 (slot 2t) and 16+4t.. (slot 2t+1) of its basis rows: two 128-bit stores per row, each instruction writing
+    // whole 32-byte sectors. (A quarter warp - g in {0,1}, t = 0..3 - reads 16-byte bank groups 9t and 9t + 4 mod 8.)
+    const uint32_t b_lane = (uint32_t)(t * RSB + ((g & 1) ? 64 + (g >> 1) * 16 : (g >> 1) * 16));   // row t, columns c0(g)..
     const bool st1 = MT > 1 && 16 + g < M;                           // this lane stores a row of the second tile
     const bool st0b = g + 8 < M, st0a = g < M;
 
@@ -186,29 +191,43 @@ gather_fwd_tile_kernel(const K1Params P) {
 
         const uint32_t xb = my_ring + (uint32_t)stage * STAGE + b_lane;
         const int b = u >> P.cpi_shift, ch = u & cpi_mask;
-        float *zp = P.z + (((size_t)b * P.p_out + p) * M + g) * I + ch * CW + 2 * t;
+        float *zp = P.z + (((size_t)b * P.p_out + p) * M + g) * I + ch * CW + 4 * t;
         float *zp8 = zp + (size_t)8 * I, *zp16 = zp + (size_t)16 * I;
         asm volatile("" : "+l"(zp), "+l"(zp8), "+l"(zp16));
 #pragma unroll
-        for (int c8 = 0; c8 < CW / 8; ++c8) {
-            float d[MT][4];
+        for (int blk = 0; blk < CW / 32; ++blk) {
+            float d[4][MT][4];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f;
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) d[j][mt][0] = d[j][mt][1] = d[j][mt][2] = d[j][mt][3] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < NK; ++ks) {
                 if (NK > 1 && ks >= nks) break;                      // warp-uniform
-                uint32_t b0, b1;
+                uint4 b0, b1;
                 switch (ks) {                                        // immediates: ks * 8 rows and the odd row
-                    case 0: b0 = lds32_o<0 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<0 * 8 * RSB + RSB>(xb + c8 * 32); break;
-                    case 1: b0 = lds32_o<1 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<1 * 8 * RSB + RSB>(xb + c8 * 32); break;
-                    default: b0 = lds32_o<2 * 8 * RSB + 0>(xb + c8 * 32); b1 = lds32_o<2 * 8 * RSB + RSB>(xb + c8 * 32); break;
+                    case 0: b0 = lds128_o<0 * 8 * RSB + 0>(xb + blk * 128); b1 = lds128_o<0 * 8 * RSB + 4 * RSB>(xb + blk * 128); break;
+                    case 1: b0 = lds128_o<1 * 8 * RSB + 0>(xb + blk * 128); b1 = lds128_o<1 * 8 * RSB + 4 * RSB>(xb + blk * 128); break;
+                    default: b0 = lds128_o<2 * 8 * RSB + 0>(xb + blk * 128); b1 = lds128_o<2 * 8 * RSB + 4 * RSB>(xb + blk * 128); break;
                 }
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) mma_tf32(d[mt], cT[mt][ks], b0, b1);
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) mma_tf32(d[j][mt], cT[mt][ks], comp(b0, j), comp(b1, j));
             }
-            if (st0a) *reinterpret_cast<float2 *>(zp + c8 * 8) = make_float2(d[0][0], d[0][1]);
-            if (st0b) *reinterpret_cast<float2 *>(zp8 + c8 * 8) = make_float2(d[0][2], d[0][3]);
-            if (MT > 1 && st1) *reinterpret_cast<float2 *>(zp16 + c8 * 8) = make_float2(d[MT - 1][0], d[MT - 1][1]);
+            // block j, fragment (c0, c1) = columns (4t + j, 16 + 4t + j) of basis row g; (c2, c3) the same of row g + 8
+            if (st0a) {
+                *reinterpret_cast<float4 *>(zp + blk * 32) = make_float4(d[0][0][0], d[1][0][0], d[2][0][0], d[3][0][0]);
+                *reinterpret_cast<float4 *>(zp + blk * 32 + 16) = make_float4(d[0][0][1], d[1][0][1], d[2][0][1], d[3][0][1]);
+            }
+            if (st0b) {
+                *reinterpret_cast<float4 *>(zp8 + blk * 32) = make_float4(d[0][0][2], d[1][0][2], d[2][0][2], d[3][0][2]);
+                *reinterpret_cast<float4 *>(zp8 + blk * 32 + 16) = make_float4(d[0][0][3], d[1][0][3], d[2][0][3], d[3][0][3]);
+            }
+            if (MT > 1 && st1) {
+                *reinterpret_cast<float4 *>(zp16 + blk * 32) = make_float4(d[0][MT - 1][0], d[1][MT - 1][0], d[2][MT - 1][0], d[3][MT - 1][0]);
+                *reinterpret_cast<float4 *>(zp16 + blk * 32 + 16) = make_float4(d[0][MT - 1][1], d[1][MT - 1][1], d[2][MT - 1][1], d[3][MT - 1][1]);
+            }
         }
         if (++stage == S) stage = 0;
     }
