@@ -733,6 +733,19 @@ def roofline(runner, steps, dump=""):
 
 def main():
     args = parse()
+    # Only the JSON line may reach stdout: libraries that print from C (NCCL's version banner, ...) write to file
+    # descriptor 1, so for the duration of the run descriptor 1 is pointed at stderr and the line goes to the saved one.
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    global print
+    out = os.fdopen(real, "w")
+
+    def print(*a, **k):                                          # noqa: A001 (the two arms print exactly one line)
+        k.setdefault("file", out)
+        import builtins
+        builtins.print(*a, **k)
+        out.flush()
     if args.impl == "reference":
         run_reference(args)
     else:

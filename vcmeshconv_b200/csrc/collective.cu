@@ -18,6 +18,8 @@
 // accumulates the shards' gradients in rank order. The barriers are per-CTA flag exchanges on the peers' flag buffers
 // (system-scope acquire/release CAS, 0 -> 1 by the sender, 1 -> 0 by the receiver), bounded: a rank that never shows
 // up aborts the launch after ~4 s instead of hanging the GPU. Plain kernel launches: capturable in the step graph.
+#include <stdlib.h>
+
 #include "adam.cuh"
 #include "common.cuh"
 
@@ -135,8 +137,11 @@ int vcm_reduce_adam_chunk(void) { return (int)(4 * vcm::kChunk4); }
 int vcm_reduce_adam_blocks(size_t n, int world) {
     if (world < 1) world = 1;
     int64_t blocks = vcm::ceil_div((int64_t)vcm::ceil_div((int64_t)(n / 4), (int64_t)vcm::kChunk4) + 1, world);
+    // few CTAs: each thread keeps kUnroll x world 16-byte peer loads in flight (measured on 2 GPUs inside the step: 16 CTAs 2.68 ms, 32 2.54, 64 2.52, 120 2.54; stand-alone more is faster
+    // - 597, 315, 115 us per 55.6 MB), and the CTAs wait at the first barrier next to the backward kernels they overlap with
+    static const int cap = [] { const char *e = getenv("VCM_COLL_BLOCKS"); const int v = e ? atoi(e) : 64; return v < 1 ? 1 : (v > 120 ? 120 : v); }();
     if (blocks < 1) blocks = 1;
-    if (blocks > 96) blocks = 96;
+    if (blocks > cap) blocks = cap;
     return (int)blocks;
 }
 
