@@ -8,7 +8,7 @@ import bench
 from vcmeshconv_b200 import functional as F_, graphVAE_train as T
 
 F_.set_precision(os.environ.get("VCM_PRECISION", "tf32"))
-pts, faces, tabs, nums = bench.build_tables(6890)
+pts, faces, tabs, nums = bench.build_tables(6890)[:4]
 enc = [tabs["pool%d" % l] for l in range(1, 7)]; dec = [tabs["unpool%d" % l] for l in range(6, 0, -1)]
 torch.manual_seed(0)
 model = T.Net_autoenc(T.make_param(enc, dec, tabs["pool0"], 6890, 0.9), faces).cuda()

@@ -18,12 +18,18 @@ for r in rows[start:]:
         recs.append((r[ki], float(r[vi].replace(",", ""))))
     except (IndexError, ValueError):
         pass
-# a step ends with the Adam launch that follows the last gradient kernel; with the early decoder-side update there
-# are two adam_dev launches per step, the first one in the middle of the backward pass
-adam = [i for i, (k, _) in enumerate(recs) if "adam_dev" in k]
-per = 2 if len(adam) >= 4 and (adam[3] - adam[1]) == (adam[2] - adam[0]) and (adam[1] - adam[0]) != (adam[2] - adam[1]) else 1
-ends = adam[per - 1::per]
-step = recs[ends[-2] + 1:ends[-1] + 1]
+# a step begins with the adam_advance launch... no: the optimizer scalars advance once per step, right before the first
+# Adam range is applied, and the step ENDS with the last adam_dev launch after it. Take the last complete step:
+# from the kernel after the previous step's last Adam launch to this step's last Adam launch.
+adv = [i for i, (k, _) in enumerate(recs) if "adam_advance" in k]
+adam = [i for i, (k, _) in enumerate(recs) if "adam_dev" in k or "reduce_adam_bcast" in k]
+ends = []
+for j, a in enumerate(adv):
+    nxt = adv[j + 1] if j + 1 < len(adv) else len(recs)
+    last = [i for i in adam if a < i < nxt]
+    if last:
+        ends.append(last[-1])
+step = recs[ends[-2] + 1:ends[-1] + 1] if len(ends) >= 2 else recs[:ends[-1] + 1]
 
 
 def key(k):

@@ -323,6 +323,27 @@ __global__ void sum_partials_kernel(const float *__restrict__ part, float *__res
     st4(out + e4, a);
 }
 
+// Many slabs of a small output: one warp per float4, lane l adds slabs l, l + 32, ... and the 32 partial sums meet in a
+// fixed butterfly order (bitwise reproducible): 148 slabs cost 5 dependent loads instead of 19 rounds of 8.
+__global__ void sum_partials_wide_kernel(const float *__restrict__ part, float *__restrict__ out, size_t n, int n_split) {
+    const size_t e4 = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
+    const int lane = threadIdx.x & 31;
+    if (e4 >= n) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = lane; k < n_split; k += 32) {
+        const float4 b = ldg4(part + (size_t)k * n + e4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+#pragma unroll
+    for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, s2);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, s2);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, s2);
+        a.w += __shfl_xor_sync(0xffffffffu, a.w, s2);
+    }
+    if (lane == 0) st4(out + e4, a);
+}
+
 // Wt[k = m*I + i][o] = W[m][o][i]  (the stacked bases [M*I, O] of the north_star)
 __global__ void transpose_bases_kernel(const float *__restrict__ W, float *__restrict__ Wt, int M, int I, int O) {
     __shared__ float tile[32][33];
@@ -385,7 +406,13 @@ DwSplit plan_dw_tc(int64_t R, int K, int O) {
         if (split > 24) split = 24;
         if (split < 1) split = 1;
     } else if (tiles < 2 * (int64_t)sm_count()) {
-        split = best_split(tiles, s.num_kb, s.num_kb / 2 < 24 ? s.num_kb / 2 : 24, sm_count());
+        // at most 24 slabs, except for small outputs (the residual projections: K*O = 32x64 floats, one output tile,
+        // 28976 rows to reduce), where 4 MB of slabs allow a split that fills the machine
+        int64_t cap = ((int64_t)1 << 20) / ((int64_t)K * O);
+        if (cap < 24) cap = 24;
+        if (cap > 2 * (int64_t)sm_count()) cap = 2 * (int64_t)sm_count();
+        if (cap > s.num_kb / 2) cap = s.num_kb / 2;
+        split = best_split(tiles, s.num_kb, (int)cap, sm_count());
     }
     s.kb_per_split = (int)ceil_div(s.num_kb, split);
     s.n_split = (int)ceil_div(s.num_kb, s.kb_per_split);
@@ -535,7 +562,10 @@ int tc_basis_bwd_dw(const float *ds, const float *z, float *dW, float *ws, int64
     if (int e = launch<MODE_DW>(bn, precision == VCM_PREC_TF32X3, grid, ma, mb, ma, p, st)) return e;
     if (p.direct) return VCM_OK;
     const size_t n = (size_t)K * O;
-    sum_partials_kernel<<<(unsigned)ceil_div((int64_t)(n / 4), 256), 256, 0, st>>>(ws, dW, n, sp.n_split);
+    if (sp.n_split > 32)
+        sum_partials_wide_kernel<<<(unsigned)ceil_div((int64_t)(n / 4) * 32, 256), 256, 0, st>>>(ws, dW, n, sp.n_split);
+    else
+        sum_partials_kernel<<<(unsigned)ceil_div((int64_t)(n / 4), 256), 256, 0, st>>>(ws, dW, n, sp.n_split);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
