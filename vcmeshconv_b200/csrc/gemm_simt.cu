@@ -34,25 +34,31 @@ struct FwdEpilogue {
     float *out;
     int P_out, O, per_point, act;
     float sy, sr;
-    __device__ __forceinline__ void operator()(int64_t r, int o, float acc) const {
-        float t = acc;
-        if (bias) t += __ldg(bias + (per_point ? (size_t)(r % P_out) * O : 0) + o);
+    __device__ __forceinline__ void operator()(int64_t r, int o, float acc) const { store(r, o, acc, load(r, o)); }
+    // split form: the loads of several elements can be issued before the first store
+    __device__ __forceinline__ float2 load(int64_t r, int o) const {
+        float2 p = make_float2(0.f, 0.f);
+        if (bias) p.x = __ldg(bias + (per_point ? (size_t)(r % P_out) * O : 0) + o);
+        if (res) p.y = __ldg(res + (size_t)r * O + o);
+        return p;
+    }
+    __device__ __forceinline__ void store(int64_t r, int o, float acc, float2 p) const {
+        const float t = acc + p.x;
         const float y = act ? elu1(t) : t;
         const size_t at = (size_t)r * O + o;
         if (y_act) y_act[at] = y;
-        float v = y * sy;
-        if (res) v = fmaf(__ldg(res + at), sr, v);
-        out[at] = v;
+        out[at] = fmaf(p.y, sr, y * sy);
     }
 };
 
 struct DzEpilogue {
     float *dz;
     int K, accumulate;
-    __device__ __forceinline__ void operator()(int64_t r, int k, float acc) const {
-        const size_t at = (size_t)r * K + k;
-        dz[at] = accumulate ? dz[at] + acc : acc;
+    __device__ __forceinline__ void operator()(int64_t r, int k, float acc) const { store(r, k, acc, load(r, k)); }
+    __device__ __forceinline__ float2 load(int64_t r, int k) const {
+        return make_float2(accumulate ? dz[(size_t)r * K + k] : 0.f, 0.f);
     }
+    __device__ __forceinline__ void store(int64_t r, int k, float acc, float2 p) const { dz[(size_t)r * K + k] = p.x + acc; }
 };
 
 // C[r, n] = sum_k A[r, k] * Bop(k, n);  A row-major [R, Kd].
@@ -133,6 +139,103 @@ __global__ void __launch_bounds__(GT) gemm_rows_kernel(const float *__restrict__
             if (n < Nd) epi(r, n, acc[i][j]);
         }
     }
+}
+
+// Skinny GEMM of the 3-channel layers (reduction <= 64, e.g. K = 17*3 = 51 -> O = 32, or O = 32 -> K = 51): the
+// 128 x 64 tiled kernel above has 227 CTAs of four barrier rounds each for 28976 rows and is bound by its own
+// latencies. Here one thread owns one row: a warp stages its 32 rows with coalesced loads in shared memory (odd row
+// stride: conflict-free), the operand tile [Kd][32 outputs] is read as warp-wide broadcasts, 32 accumulators per thread,
+// no barrier after the prologue. blockIdx.y walks 32-output chunks.
+constexpr int SK_WARPS = 4;
+template <bool B_KN, typename Epi>
+__global__ void __launch_bounds__(32 * SK_WARPS) gemm_rows_skinny_kernel(const float *__restrict__ A,
+                                                                         const float *__restrict__ W, int64_t R, int Kd,
+                                                                         int Nd, int I, int O, Epi epi) {
+    extern __shared__ __align__(16) float sk_smem[];
+    const int ks = (Kd | 1) < 33 ? 33 : (Kd | 1);            // odd stride of the staged rows (>= 33: reused as [32][33])
+    float *Ws = sk_smem;                                     // [Kd][32]
+    float *As = Ws + Kd * 32 + (threadIdx.x >> 5) * 32 * ks; // this warp's [32][ks]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = blockIdx.y * 32;
+    for (int e = threadIdx.x; e < Kd * 32; e += blockDim.x) {
+        int kk, nn;
+        if (B_KN) { kk = e % Kd; nn = e / Kd; }              // contiguous along the basis index
+        else      { nn = e & 31; kk = e >> 5; }
+        const int ng = n0 + nn;
+        float v = 0.f;
+        if (ng < Nd) v = B_KN ? __ldg(W + basis_addr(kk, ng, I, O)) : __ldg(W + basis_addr(ng, kk, I, O));
+        Ws[kk * 32 + nn] = v;
+    }
+    __syncthreads();
+    const int64_t n_groups = (R + 31) / 32;
+    for (int64_t grp = (int64_t)blockIdx.x * SK_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * SK_WARPS) {
+        const int64_t r0 = grp * 32;
+        const int n_rows = (int)(R - r0 < 32 ? R - r0 : 32);
+        const float *src = A + (size_t)r0 * Kd;
+        __syncwarp();
+        // coalesced (lanes stride one row), as 4-byte cp.async: all copies of the tile are in flight at once, no
+        // load -> store register dependency per element
+        {
+            const uint32_t as_u = (uint32_t)__cvta_generic_to_shared(As);
+            for (int row = 0; row < n_rows; ++row)
+                for (int k = lane; k < Kd; k += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(as_u + (uint32_t)(row * ks + k) * 4u),
+                                 "l"(src + row * Kd + k) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            for (int row = n_rows; row < 32; ++row)
+                for (int k = lane; k < Kd; k += 32) As[row * ks + k] = 0.f;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        const float *ar = As + lane * ks;
+        for (int k = 0; k < Kd; ++k) {
+            const float a = ar[k];
+            const float4 *w4 = reinterpret_cast<const float4 *>(Ws + k * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w = w4[j4];
+                acc[4 * j4 + 0] = fmaf(a, w.x, acc[4 * j4 + 0]);
+                acc[4 * j4 + 1] = fmaf(a, w.y, acc[4 * j4 + 1]);
+                acc[4 * j4 + 2] = fmaf(a, w.z, acc[4 * j4 + 2]);
+                acc[4 * j4 + 3] = fmaf(a, w.w, acc[4 * j4 + 3]);
+            }
+        }
+        // transpose through the (now free) row tile: lane = output column, so that the epilogue's loads and stores
+        // are coalesced 128-byte rows
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) As[lane * 33 + j] = acc[j];
+        __syncwarp();
+        if (n0 + lane < Nd) {
+            int i = 0;
+            for (; i + 8 <= n_rows; i += 8) {                // the epilogue's own loads (bias, residual) 8 rows ahead
+                float2 pre[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pre[u] = epi.load(r0 + i + u, n0 + lane);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) epi.store(r0 + i + u, n0 + lane, As[(i + u) * 33 + lane], pre[u]);
+            }
+            for (; i < n_rows; ++i) epi(r0 + i, n0 + lane, As[i * 33 + lane]);
+        }
+    }
+}
+
+template <bool B_KN, typename Epi>
+int launch_skinny(const float *A, const float *W, int64_t R, int Kd, int Nd, int I, int O, const Epi &epi, cudaStream_t st) {
+    const size_t smem = ((size_t)Kd * 32 + (size_t)SK_WARPS * 32 * ((Kd | 1) < 33 ? 33 : (Kd | 1))) * sizeof(float);
+    int64_t bx = ceil_div(ceil_div(R, 32), SK_WARPS);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (bx > cap) bx = cap;
+    dim3 grid((unsigned)bx, (unsigned)ceil_div(Nd, 32));
+    gemm_rows_skinny_kernel<B_KN, Epi><<<grid, 32 * SK_WARPS, smem, st>>>(A, W, R, Kd, Nd, I, O, epi);
+    return VCM_OK;
+}
+static bool skinny_ok(int Kd, int Nd) {
+    static const int on = [] { const char *e = getenv("VCM_SKINNY_GEMM"); return e ? atoi(e) : 1; }();
+    return on && Kd <= 64 && Nd <= 128;
 }
 
 // K2 for a handful of output channels (last decoder layer, O = 3): one warp per
@@ -358,6 +461,8 @@ int simt_basis_fwd(const float *z, const float *W, const float *bias, int per_po
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
         k<<<(unsigned)blocks, 256, smem, st>>>(z, W, R, K, I, O, epi);
+    } else if (skinny_ok(K, O)) {
+        launch_skinny<true, FwdEpilogue>(z, W, R, K, O, I, O, epi, st);
     } else {
         dim3 grid((unsigned)ceil_div(R, BM), (unsigned)ceil_div(O, BN));
         gemm_rows_kernel<true, FwdEpilogue><<<grid, GT, 0, st>>>(z, W, R, K, O, I, O, epi);
@@ -370,8 +475,12 @@ int simt_basis_bwd_dz(const float *ds, const float *W, float *dz, int64_t R, int
                       cudaStream_t st) {
     const int K = M * I;
     DzEpilogue epi{dz, K, accumulate};
-    dim3 grid((unsigned)ceil_div(R, BM), (unsigned)ceil_div(K, BN));
-    gemm_rows_kernel<false, DzEpilogue><<<grid, GT, 0, st>>>(ds, W, R, O, K, I, O, epi);
+    if (skinny_ok(O, K)) {
+        launch_skinny<false, DzEpilogue>(ds, W, R, O, K, I, O, epi, st);
+    } else {
+        dim3 grid((unsigned)ceil_div(R, BM), (unsigned)ceil_div(K, BN));
+        gemm_rows_kernel<false, DzEpilogue><<<grid, GT, 0, st>>>(ds, W, R, O, K, I, O, epi);
+    }
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }
