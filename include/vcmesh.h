@@ -155,6 +155,12 @@ VCM_API int vcm_coeff_grad_ex(const vcm_tables *t, const float *dz, const float 
  * Replaces the index_add_ scatter autograd runs for graphVAESSW.py:122. */
 VCM_API int vcm_scatter_rev(const vcm_tables *t, const float *dG, float *dx, int B, int I, int accumulate,
                             void *stream);
+/* K6 with one coefficient per edge (M = 1 gathers: residual pool / un-pool graphVAESSW.py:151-159, loss gathers):
+ * dx[b,q,:] (+)= sum_{slot in rev(q)} coef[slot] * dy[b, slot / N, :], coef [P_out, N] (padding slots are never
+ * read), dy [B, P_out, I]. The autograd mirror of index_select + weighted sum without materialising the per-edge
+ * gradient. */
+VCM_API int vcm_scatter_rev_scaled(const vcm_tables *t, const float *dy, const float *coef, float *dx, int B, int I,
+                                   int accumulate, void *stream);
 
 /* Residual edge weights, graphVAESSW.py:155-157:
  *   pn[p,n] = |p_nb[p,n]| * mask / (sum_n |p_nb[p,n]| * mask + 1e-8)

@@ -57,3 +57,35 @@ def test_gather_contract_tile_kernel(case):
     if n_max <= 24:                                                  # the tile kernel served it (wider tables: fp32 kernel)
         assert rel_err(z, want) < 2e-5
     assert rel_err(z, z32) < 3e-3
+
+
+@pytest.mark.parametrize("case", [(16, 120, 77, 9, 64), (4, 300, 40, 47, 256), (16, 60, 200, 12, 3)],
+                         ids=lambda c: "B%d_P%d-%d_N%d_I%d" % c)
+def test_scaled_reverse_scatter_equals_coeff_grad_plus_scatter(case):
+    """M = 1 gathers (residual pool / un-pool): dx[b,q,:] = sum_{slot in rev(q)} coef[slot] * dy[b, slot // N, :]
+    (vcm_scatter_rev_scaled, no per-edge gradient) against the fp64 reference and against K5 (dG) + K6."""
+    B, p_in, p_out, n_max, I = case
+    tab, ids = random_table(p_in, p_out, n_max, seed=3 * p_out + n_max)
+    t = DeviceTables(tab, p_in)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    dy = torch.randn(B, p_out, I, device="cuda", generator=g)
+    coef = torch.randn(p_out, n_max, device="cuda", generator=g)
+    x = torch.randn(B, p_in, I, device="cuda", generator=g)
+    L = _lib.lib()
+    dx = torch.full((B, p_in, I), float("nan"), device="cuda")
+    dx2 = torch.full_like(dx, float("nan"))
+    _lib.check(L.vcm_scatter_rev_scaled(t.handle, dy.data_ptr(), coef.data_ptr(), dx.data_ptr(), B, I, 0, _lib.stream_ptr()))
+    dG = torch.empty(B, p_out, n_max, I, device="cuda")
+    _lib.check(L.vcm_coeff_grad(t.handle, dy.data_ptr(), x.data_ptr(), coef.data_ptr(), None, dG.data_ptr(), None, B, I, 1,
+                                _lib.stream_ptr()))
+    _lib.check(L.vcm_scatter_rev(t.handle, dG.data_ptr(), dx2.data_ptr(), B, I, 0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    idt = torch.from_numpy(ids).cuda()
+    real = (idt != p_in)
+    want = torch.zeros(B, p_in + 1, I, dtype=torch.float64, device="cuda")
+    contrib = (coef.double() * real)[None, :, :, None] * dy.double()[:, :, None, :]          # [B, P, N, I]
+    want.index_add_(1, idt.reshape(-1), contrib.reshape(B, p_out * n_max, I))
+    want = want[:, :p_in]
+    assert torch.isfinite(dx).all()
+    assert rel_err(dx, want) < 1e-6
+    assert rel_err(dx, dx2) < 1e-6

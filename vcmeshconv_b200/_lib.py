@@ -44,6 +44,7 @@ SIGNATURES = {
     "vcm_coeff_grad_workspace_ex": (_sz, [_p, _i, _i, _i, _i]),
     "vcm_coeff_grad_ex": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "vcm_scatter_rev": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "vcm_scatter_rev_scaled": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "vcm_edge_weights_fwd": (_i, [_p, _p, _p, _p]),
     "vcm_edge_weights_bwd": (_i, [_p, _p, _p, _p, _p]),
     "vcm_basis_fwd_workspace": (_sz, [_i64, _i, _i, _i, _i]),

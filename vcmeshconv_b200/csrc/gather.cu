@@ -379,6 +379,63 @@ scatter_rev_kernel(const int32_t *__restrict__ rev_ptr, const int32_t *__restric
     o.store(dst);
 }
 
+// K6 for one coefficient per edge (M = 1: the residual pool / un-pool of graphVAESSW.py:151-159, the Laplacian and the
+// face gathers of the losses): dx[b,q,:] = sum_{slot in rev(q)} coef[slot] * dy[b, slot / N, :]. The per-edge gradient
+// dG[b,p,n,:] = coef[p,n] * dy[b,p,:] is never written: the rows of dy (a few MB, L2-resident) are read through the
+// reverse list directly - for a pooling layer with ~47 neighbours that is 1/47 of the bytes of dG, twice.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+scatter_rev_scaled_kernel(const int32_t *__restrict__ rev_ptr, const int32_t *__restrict__ rev_slot,
+                          const float *__restrict__ coef, const float *__restrict__ dy, float *__restrict__ dx, int p_in,
+                          int p_out, int n_max, int I, ColumnGeom g, int accumulate) {
+    const int tid = threadIdx.x;
+    const int v = tid / g.CB;
+    const int q = blockIdx.x * g.TP + v;
+    const int c = blockIdx.y * g.CB + (tid - v * g.CB);
+    if (q >= p_in || c >= g.C) return;
+    const int b = c / g.IV, i0 = (c - b * g.IV) * VEC;
+    const float *src = dy + (size_t)b * p_out * I + i0;
+    float *dst = dx + ((size_t)b * p_in + q) * I + i0;
+    const int e0 = __ldg(rev_ptr + q), e1 = __ldg(rev_ptr + q + 1);
+    float acc[VEC];
+    if (accumulate) {
+        Vec<VEC> t;
+        t.load(dst);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = t.v[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    }
+    int e = e0;
+    for (; e + 4 <= e1; e += 4) {                         // 4 independent gathers in flight
+        Vec<VEC> t[4];
+        float w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int slot = __ldg(rev_slot + e + u);
+            w[u] = __ldg(coef + slot);
+            t[u].load(src + (size_t)(slot / n_max) * I);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w[u], t[u].v[j], acc[j]);
+    }
+    for (; e < e1; ++e) {
+        const int slot = __ldg(rev_slot + e);
+        const float w = __ldg(coef + slot);
+        Vec<VEC> t;
+        t.load(src + (size_t)(slot / n_max) * I);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, t.v[j], acc[j]);
+    }
+    Vec<VEC> o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o.v[j] = acc[j];
+    o.store(dst);
+}
+
 // ------------------------------------------------- residual edge weights ----
 // one warp per output vertex, lanes over the neighbour slots (fixed-order butterfly sums)
 __device__ __forceinline__ float warp_sum(float v) {
@@ -608,6 +665,26 @@ int vcm_scatter_rev(const vcm_tables *h, const float *dG, float *dx, int B, int 
     else
         scatter_rev_kernel<1><<<grid, kThreads, 0, st>>>(t->rev_ptr, t->rev_slot, dG, dx, t->p_in, t->p_out, t->n_max,
                                                          I, g, accumulate);
+    VCM_LAUNCH_CHECK();
+    return VCM_OK;
+}
+
+int vcm_scatter_rev_scaled(const vcm_tables *h, const float *dy, const float *coef, float *dx, int B, int I,
+                           int accumulate, void *stream) {
+    const Tables *t = as_tables(h);
+    if (int e = check_common(t, B, I, 1)) return e;
+    VCM_DEVPTR(dy); VCM_DEVPTR(coef); VCM_DEVPTR(dx);
+    if (t->p_in == 0) return VCM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v4 = I % 4 == 0 && aligned16(dy) && aligned16(dx);
+    ColumnGeom g = column_geom(B, I, v4 ? 4 : 1, 8);
+    dim3 grid((unsigned)ceil_div(t->p_in, g.TP), (unsigned)ceil_div(g.C, g.CB));
+    if (v4)
+        scatter_rev_scaled_kernel<4><<<grid, kThreads, 0, st>>>(t->rev_ptr, t->rev_slot, coef, dy, dx, t->p_in, t->p_out,
+                                                                t->n_max, I, g, accumulate);
+    else
+        scatter_rev_scaled_kernel<1><<<grid, kThreads, 0, st>>>(t->rev_ptr, t->rev_slot, coef, dy, dx, t->p_in, t->p_out,
+                                                                t->n_max, I, g, accumulate);
     VCM_LAUNCH_CHECK();
     return VCM_OK;
 }

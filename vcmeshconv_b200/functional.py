@@ -71,6 +71,10 @@ def _grad_target(t, needed=True):
     return buf.view(t.shape)
 
 
+# M = 1 gathers (residual pool / un-pool, loss gathers): dx without the per-edge gradient (VCM_M1_DIRECT=0: K5 + K6)
+_m1_direct = __import__("os").environ.get("VCM_M1_DIRECT", "1") == "1"
+
+
 def begin_step(params):
     """Called by the trainer before every (captured or eager) backward: each parameter may be written
     directly once; a second use falls back to autograd accumulation."""
@@ -117,6 +121,19 @@ def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
         return (torch.zeros_like(x) if need_dx else None), (torch.zeros_like(A) if need_dA else None)
     dz = _req(dz, "dz")
     L = _lib.lib()
+    if M == 1 and need_dx and _m1_direct:
+        # one coefficient per edge: dx comes straight from dz through the reverse list (vcm_scatter_rev_scaled), the
+        # per-edge gradient dG = A * dz is never written; K5 only produces dA
+        st = _lib.stream_ptr()
+        nnz = t.nnz
+        tag = "P%d>%d I%d M1 direct" % (p_in, t.p_out, I)
+        dx = torch.empty_like(x)
+        _lib.call("vcm_scatter_rev_scaled", t.handle, _ptr(dz), _ptr(A), _ptr(dx), B, I, 0, st,
+                  nbytes=4 * (dz.numel() + 2 * nnz + (p_in + 1) + x.numel()), flops=2 * B * nnz * I, tag=tag)
+        if not need_dA:
+            return dx, None
+        _, dA = _gather_backward(t, x, A, dz, False, True, dA_target, precision)
+        return dx, dA
     direct_dA = need_dA and dA_target is not None
     dA = (dA_target if direct_dA else torch.empty_like(A)) if need_dA else None
     dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
