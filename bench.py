@@ -223,6 +223,7 @@ class CpuArm:
                 self.layer = ref.ReferenceLayer(table, cfg["cin"], cfg["cout"], M, len(pts), cfg["residual"], seed=0)
             else:
                 self.layer = orc.Layer(table, cfg["cin"], cfg["cout"], len(pts), cfg["residual"])
+                self.layer.counts, self.layer.ids = self.layer.counts.to(device), self.layer.ids.to(device)
                 self.params = {k: v.to(device).requires_grad_(True) for k, v in orc.init_layer_params(
                     table, cfg["cin"], cfg["cout"], M, len(pts), True, cfg["residual"], g).items()}
                 self.coeffs = orc.init_coeffs(table, M, g).to(device).requires_grad_(True)
