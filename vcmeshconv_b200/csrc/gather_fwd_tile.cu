@@ -52,6 +52,9 @@ __device__ __forceinline__ uint4 lds128_o(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
     return v;
 }
+__device__ __forceinline__ void stg128(float *p, float a, float b, float c, float d) {       // explicit global space
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
 // 16-byte cp.async, skipped when off == 0xFFFFFFFF (predicated inside the asm: no branch around it)
 template <int DOFF>
@@ -217,16 +220,16 @@ gather_fwd_tile_kernel(const K1Params P) {
             }
             // block j, fragment (c0, c1) = columns (4t + j, 16 + 4t + j) of basis row g; (c2, c3) the same of row g + 8
             if (st0a) {
-                *reinterpret_cast<float4 *>(zp + blk * 32) = make_float4(d[0][0][0], d[1][0][0], d[2][0][0], d[3][0][0]);
-                *reinterpret_cast<float4 *>(zp + blk * 32 + 16) = make_float4(d[0][0][1], d[1][0][1], d[2][0][1], d[3][0][1]);
+                stg128(zp + blk * 32, d[0][0][0], d[1][0][0], d[2][0][0], d[3][0][0]);
+                stg128(zp + blk * 32 + 16, d[0][0][1], d[1][0][1], d[2][0][1], d[3][0][1]);
             }
             if (st0b) {
-                *reinterpret_cast<float4 *>(zp8 + blk * 32) = make_float4(d[0][0][2], d[1][0][2], d[2][0][2], d[3][0][2]);
-                *reinterpret_cast<float4 *>(zp8 + blk * 32 + 16) = make_float4(d[0][0][3], d[1][0][3], d[2][0][3], d[3][0][3]);
+                stg128(zp8 + blk * 32, d[0][0][2], d[1][0][2], d[2][0][2], d[3][0][2]);
+                stg128(zp8 + blk * 32 + 16, d[0][0][3], d[1][0][3], d[2][0][3], d[3][0][3]);
             }
             if (MT > 1 && st1) {
-                *reinterpret_cast<float4 *>(zp16 + blk * 32) = make_float4(d[0][MT - 1][0], d[1][MT - 1][0], d[2][MT - 1][0], d[3][MT - 1][0]);
-                *reinterpret_cast<float4 *>(zp16 + blk * 32 + 16) = make_float4(d[0][MT - 1][1], d[1][MT - 1][1], d[2][MT - 1][1], d[3][MT - 1][1]);
+                stg128(zp16 + blk * 32, d[0][MT - 1][0], d[1][MT - 1][0], d[2][MT - 1][0], d[3][MT - 1][0]);
+                stg128(zp16 + blk * 32 + 16, d[0][MT - 1][1], d[1][MT - 1][1], d[2][MT - 1][1], d[3][MT - 1][1]);
             }
         }
         if (++stage == S) stage = 0;
