@@ -146,6 +146,11 @@ VCM_API int vcm_coeff_grad(const vcm_tables *t, const float *dz, const float *x,
  * and an mbarrier pipeline (coeff_grad_tma_kernel, the TF32-mode default), 1 = tensor-pipe kernel staged with
  * cp.async (coeff_grad_mma_kernel), 0 = fp32 CUDA-core kernel (coeff_grad_kernel). bench.py groups its timings by it. */
 VCM_API int vcm_coeff_grad_variant(const vcm_tables *t, int B, int I, int M, int precision);
+/* Same, knowing which outputs are asked for: 3 = coeff_grad_small_kernel (dA only, I <= 8 channels and B*I <= 256
+ * columns per vertex, tensor-core modes: one warp per vertex, mma.sync fragments loaded straight from global memory -
+ * the 3-channel input layer and the M = 1 residual paths over xyz), otherwise the value above. */
+VCM_API int vcm_coeff_grad_variant_ex(const vcm_tables *t, int B, int I, int M, int precision, int want_dA,
+                                      int want_dG);
 VCM_API size_t vcm_coeff_grad_workspace_ex(const vcm_tables *t, int B, int I, int M, int precision);
 VCM_API int vcm_coeff_grad_ex(const vcm_tables *t, const float *dz, const float *x, const float *A, float *dA,
                               float *dG, float *workspace, int B, int I, int M, int precision, void *stream);

@@ -93,3 +93,42 @@ def test_optional_outputs_and_determinism():
     real = torch.from_numpy(ids != p_in).cuda()
     assert torch.equal(dA, dA2) and torch.equal(dA, dA3)                   # fixed-order reductions: bitwise reproducible
     assert torch.equal(dG[:, real], dG2[:, real]) and torch.equal(dG[:, real], dG3[:, real])
+
+
+SMALL_CASES = [  # B, p_in, p_out, n_max, M, I   (dA only: coeff_grad_small_kernel)
+    (16, 500, 130, 35, 17, 3),          # the 3-channel input layer: three neighbour blocks
+    (16, 130, 500, 12, 1, 3),           # residual path over xyz: M = 1, one block
+    (64, 300, 90, 21, 17, 3),           # C3 batch: 192 columns, 24 k-steps
+    (5, 80, 70, 58, 17, 3),             # 15 columns (partial k-step), four neighbour blocks
+    (7, 60, 60, 9, 24, 1),              # one channel, M = 24
+    (3, 60, 60, 16, 8, 8),              # I = 8, M = 8 (one basis block)
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=lambda c: "B%d_P%d-%d_N%d_M%d_I%d" % c)
+@pytest.mark.parametrize("prec", ["tf32", "tf32x3"])
+def test_coeff_grad_small_channels(case, prec):
+    B, p_in, p_out, n_max, M, I = case
+    tab, ids = random_table(p_in, p_out, n_max, seed=p_out + n_max)
+    t = DeviceTables(tab, p_in)
+    L = _lib.lib()
+    assert L.vcm_coeff_grad_variant_ex(t.handle, B, I, M, _lib.PRECISIONS[prec], 1, 0) == 3
+    assert L.vcm_coeff_grad_variant_ex(t.handle, B, I, M, _lib.PRECISIONS[prec], 1, 1) != 3
+    assert L.vcm_coeff_grad_variant_ex(t.handle, B, I, M, _lib.PRECISIONS["fp32"], 1, 0) == 0
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dz = torch.randn(B, p_out, M, I, device="cuda", generator=g)
+    x = torch.randn(B, p_in, I, device="cuda", generator=g)
+    A = torch.randn(p_out, n_max, M, device="cuda", generator=g)
+    dA, _ = run(t, dz.view(B, p_out, M * I), x, A, B, I, M, _lib.PRECISIONS[prec], want_dG=False)
+    wA, _, real = reference(dz, x, A, ids, p_in)
+    assert torch.isfinite(dA).all()
+    assert (dA[~real] == 0).all()                                          # padding slots: exact zeros
+    assert rel_err(dA, wA) < (3e-3 if prec == "tf32" else 1e-5)
+    if prec == "tf32":
+        tA, _, _ = reference(trunc_tf32(dz), trunc_tf32(x), A, ids, p_in)
+        assert rel_err(dA, tA) < 2e-5                                      # pins the fragment mapping
+    dA2, _ = run(t, dz.view(B, p_out, M * I), x, A, B, I, M, _lib.PRECISIONS[prec], want_dG=False)
+    assert torch.equal(dA, dA2)
+    # and the fp32 kernel agrees (the same call in fp32 mode)
+    dA3, _ = run(t, dz.view(B, p_out, M * I), x, A, B, I, M, _lib.PRECISIONS["fp32"], want_dG=False)
+    assert rel_err(dA3, wA) < 1e-5

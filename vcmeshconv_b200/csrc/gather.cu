@@ -18,6 +18,7 @@
 // bitwise reproducible and there are no atomics.
 #include "common.cuh"
 #include "k1_tile.h"
+#include "k5_small.h"
 #include "k5_tma.h"
 
 namespace vcm {
@@ -1520,6 +1521,11 @@ static bool use_grad_mma(const vcm::Tables *t, int B, int I, int M, int precisio
     return !(use_mma >= 2 && (pl->nt16 > 2 || precision != VCM_PREC_TF32));
 }
 
+int vcm_coeff_grad_variant_ex(const vcm_tables *h, int B, int I, int M, int precision, int want_dA, int want_dG) {
+    if (vcm::k5_small_ok(vcm::as_tables(h), B, I, M, precision, want_dA != 0, want_dG != 0)) return 3;
+    return vcm_coeff_grad_variant(h, B, I, M, precision);
+}
+
 int vcm_coeff_grad_variant(const vcm_tables *h, int B, int I, int M, int precision) {
     vcm::MmaGradPlan pl;
     vcm::K5TmaPlan tp;
@@ -1533,6 +1539,12 @@ int vcm_coeff_grad_ex(const vcm_tables *h, const float *dz, const float *x, cons
     const Tables *t = as_tables(h);
     MmaGradPlan pl;
     K5TmaPlan tp;
+    if (k5_small_ok(t, B, I, M, precision, dA != nullptr, dG != nullptr)) {
+        // a handful of channels, dA only: one warp per vertex, fragments straight from global memory
+        VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(dA);
+        if (int e0 = check_common(t, B, I, M)) return e0;
+        return k5_small_launch(t, dz, x, dA, B, I, M, precision, (cudaStream_t)stream);
+    }
     if (k5_tma_plan(t, B, I, M, precision, &tp)) {
         VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR_OPT(dA); VCM_DEVPTR_OPT(dG); VCM_DEVPTR_OPT(ws);
         VCM_CHECK(dA != nullptr || dG != nullptr, "nothing to compute: dA and dG are both NULL");

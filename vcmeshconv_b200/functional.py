@@ -144,7 +144,8 @@ def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
     nnz = t.nnz
     # the tag names the layer shape and the kernel that serves it (bench.py groups timings by kernel)
     tag = "P%d>%d I%d M%d %s" % (p_in, t.p_out, I, M,
-                                 ("fp32", "mma", "tma")[L.vcm_coeff_grad_variant(t.handle, B, I, M, precision)])
+                                 ("fp32", "mma", "tma", "small")[L.vcm_coeff_grad_variant_ex(
+                                     t.handle, B, I, M, precision, int(need_dA), int(need_dx))])
     gb = 4 * B * nnz * I
     if split:
         # Only dG is on the backward chain (dG -> K6 -> dx -> next layer); dA goes straight into the flat gradient
