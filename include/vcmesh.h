@@ -193,7 +193,12 @@ VCM_API int vcm_basis_fwd(const float *z, const float *W, const float *bias, int
  * HBM round trip. `z` (fp32 [B,P_out,M*I]) is optional: pass a buffer when the backward pass needs it (written
  * once by TMA stores), NULL for inference. Everything else as vcm_basis_fwd. Available for precision
  * VCM_PREC_TF32, B % 16 == 0, B <= 128, M <= 17, I % 8 == 0, O % 32 == 0 (vcm_conv_fwd_fused_supported);
- * other shapes use vcm_gather_contract_fwd + vcm_basis_fwd. */
+ * other shapes use vcm_gather_contract_fwd + vcm_basis_fwd.
+ * The 3-channel layers (I = 3, O = 32 or 64, M <= 24, N <= 64; VCM_PREC_TF32 and VCM_PREC_TF32X3) are served by a
+ * second kernel with one warp per vertex and mma.sync fragments loaded straight from global memory
+ * (fused_fwd_small_kernel): vcm_conv_fwd_fused_kind returns 2 for them, 1 for the tcgen05 kernel, 0 = unsupported.
+ * The nn.Module layer uses kind 2 by default (the forward chain loses a launch and the round trip of z). */
+VCM_API int vcm_conv_fwd_fused_kind(const vcm_tables *t, int B, int M, int I, int O, int precision);
 VCM_API int vcm_conv_fwd_fused_supported(const vcm_tables *t, int B, int M, int I, int O, int precision);
 VCM_API size_t vcm_conv_fwd_fused_workspace(const vcm_tables *t, int B, int M, int I, int O, int precision);
 VCM_API int vcm_conv_fwd_fused(const vcm_tables *t, const float *x, const float *A, const float *W,

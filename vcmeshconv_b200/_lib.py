@@ -51,6 +51,7 @@ SIGNATURES = {
     "vcm_basis_fwd_workspace": (_sz, [_i64, _i, _i, _i, _i]),
     "vcm_basis_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p]),
     "vcm_conv_fwd_fused_supported": (_i, [_p, _i, _i, _i, _i, _i]),
+    "vcm_conv_fwd_fused_kind": (_i, [_p, _i, _i, _i, _i, _i]),
     "vcm_conv_fwd_fused_workspace": (_sz, [_p, _i, _i, _i, _i, _i]),
     "vcm_conv_fwd_fused": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _p]),
     "vcm_bias_act_fwd": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p]),

@@ -100,14 +100,22 @@ int vcm_basis_bwd_dw(const float *ds, const float *z, float *dW, float *workspac
     return simt_basis_bwd_dw(ds, z, dW, workspace, rows, M, I, O, st);
 }
 
-int vcm_conv_fwd_fused_supported(const vcm_tables *tables, int B, int M, int I, int O, int precision) {
+int vcm_conv_fwd_fused_kind(const vcm_tables *tables, int B, int M, int I, int O, int precision) {
     const Tables *t = as_tables(tables);
-    return t != nullptr && B > 0 && fused_fwd_supported(t, B, M, I, O, precision) ? 1 : 0;
+    if (t == nullptr || B <= 0) return 0;
+    if (fused_small_supported(t, B, M, I, O, precision)) return 2;
+    return fused_fwd_supported(t, B, M, I, O, precision) ? 1 : 0;
+}
+
+int vcm_conv_fwd_fused_supported(const vcm_tables *tables, int B, int M, int I, int O, int precision) {
+    return vcm_conv_fwd_fused_kind(tables, B, M, I, O, precision) != 0 ? 1 : 0;
 }
 
 size_t vcm_conv_fwd_fused_workspace(const vcm_tables *tables, int B, int M, int I, int O, int precision) {
     const Tables *t = as_tables(tables);
-    if (t == nullptr || B <= 0 || !fused_fwd_supported(t, B, M, I, O, precision)) return 0;
+    if (t == nullptr || B <= 0 || fused_small_supported(t, B, M, I, O, precision) ||
+        !fused_fwd_supported(t, B, M, I, O, precision))
+        return 0;
     return fused_fwd_workspace(t, B, M, I, O);
 }
 
@@ -121,6 +129,14 @@ int vcm_conv_fwd_fused(const vcm_tables *tables, const float *x, const float *A,
     if (int e = check_gemm((int64_t)B * t->p_out, M, I, O, precision)) return e;
     VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR(W); VCM_DEVPTR(out);
     VCM_DEVPTR_OPT(bias); VCM_DEVPTR_OPT(res); VCM_DEVPTR_OPT(y_act); VCM_DEVPTR_OPT(z); VCM_DEVPTR_OPT(workspace);
+    if (fused_small_supported(t, B, M, I, O, precision)) {
+        // scalar operand loads; only the epilogue's float2 accesses need alignment
+        VCM_CHECK(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(y_act) |
+                    reinterpret_cast<uintptr_t>(res)) & 7) == 0, "out, y_act and res must be 8-byte aligned");
+        if (t->p_out == 0) return VCM_OK;
+        return fused_small(t, x, A, W, bias, bias_per_point, res, y_act, out, z, B, M, I, O, act, scale_y, scale_res,
+                           precision, (cudaStream_t)stream);
+    }
     VCM_CHECK(aligned16(x) && aligned16(W) && aligned16(out) && (z == nullptr || aligned16(z)),
               "x, W, out and z must be 16-byte aligned");
     if (!fused_fwd_supported(t, B, M, I, O, precision))

@@ -40,4 +40,10 @@ int fused_fwd(const Tables *t, const float *x, const float *A, const float *W, c
               const float *res, float *y_act, float *out, float *z, float *ws, int B, int M, int I, int O, int act,
               float sy, float sr, cudaStream_t st);
 
+// K1 + K2 fused for the 3-channel layers, one warp per vertex (fused_fwd_small.cu)
+bool fused_small_supported(const Tables *t, int B, int M, int I, int O, int precision);
+int fused_small(const Tables *t, const float *x, const float *A, const float *W, const float *bias, int per_point,
+                const float *res, float *y_act, float *out, float *z, int B, int M, int I, int O, int act, float sy,
+                float sr, int precision, cudaStream_t st);
+
 }  // namespace vcm

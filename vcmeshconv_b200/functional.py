@@ -651,6 +651,12 @@ def basis_gemm(z, weights, bias, res, M, I, O, act, scale_y=1.0, scale_res=0.0, 
 fused_conv_enabled = __import__("os").environ.get("VCM_FUSED_FWD", "0") == "1"
 
 
+def fused_conv_kind(tables, B, M, I, O, precision=None):
+    """0 = K1 + K2, 1 = tcgen05 fused kernel (opt-in), 2 = the 3-channel kernel (used by default)."""
+    prec = _precision if precision is None else precision
+    return int(_lib.lib().vcm_conv_fwd_fused_kind(tables.handle, B, M, I, O, prec))
+
+
 def fused_conv_supported(tables, B, M, I, O, precision=None):
     prec = _precision if precision is None else precision
     return bool(_lib.lib().vcm_conv_fwd_fused_supported(tables.handle, B, M, I, O, prec))

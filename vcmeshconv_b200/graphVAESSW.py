@@ -111,9 +111,10 @@ class LASMConvssw(nn.Module):
         if self.project_first:
             return self._forward_project_first(in_pc, raw_w_weights, is_final_layer)
         M, I, O = self.weight_num, self.in_channel, self.out_channel
-        if F_.fused_conv_enabled and in_pc.is_cuda and in_pc.dim() == 3 and F_.fused_conv_supported(t, in_pc.shape[0], M, I, O):
+        kind = F_.fused_conv_kind(t, in_pc.shape[0], M, I, O) if in_pc.is_cuda and in_pc.dim() == 3 else 0
+        if kind == 2 or (kind == 1 and F_.fused_conv_enabled):
             # K1 + K2 in one launch: z stays on chip (it is stored once only when a backward pass follows)
-            res, sy, sr = self._residual(in_pc, t)
+            res, sy, sr = self._residual_join(self._residual_fork(in_pc, t))
             return F_.fused_conv(in_pc, raw_w_weights, self.weights, self.bias, res, t, M, I, O, not is_final_layer,
                                  sy, sr)
         branch = self._residual_fork(in_pc, t)
