@@ -250,7 +250,12 @@ class DataParallelTrainer:
         self.da_stream = (torch.cuda.Stream(self.flat.flat_p.device)
                           if self.flat.flat_p.is_cuda and os.environ.get("VCM_SPLIT_K5", "0") == "1" else None)
         # residual branch of every layer on its own stream (forward, and through autograd its backward)
-        self.res_stream = (torch.cuda.Stream(self.flat.flat_p.device)
+        # Stream priorities (VCM_STREAM_PRIO=0 turns them off): the backward chain and the residual branches that rejoin
+        # it run at high priority, the branches nothing waits for until the optimizer (dW GEMMs, dA halves, stacked
+        # bases, early Adam) at the default one, so that a wide off-chain kernel does not keep the chain's next kernel
+        # out of the SMs. Captured kernel nodes inherit the priority of the stream they were captured on.
+        self._prio = -1 if os.environ.get("VCM_STREAM_PRIO", "1") == "1" else 0
+        self.res_stream = (torch.cuda.Stream(self.flat.flat_p.device, priority=self._prio)
                            if self.flat.flat_p.is_cuda and os.environ.get("VCM_RES_STREAM", "1") == "1" else None)
         # decoder-side all-reduce + Adam next to the encoder's backward pass (VCM_EARLY_UPDATE=0 turns it off)
         self.early_stream = (torch.cuda.Stream(self.flat.flat_p.device)
@@ -602,7 +607,8 @@ class DataParallelTrainer:
         # process group that capture hung on 2 x B200 in this image (torch 2.11 / NCCL 2.28), so it is not the default.
         nccl_in_graph = self.world == 1 or os.environ.get("VCM_GRAPH_NCCL", "0") == "1" or self._symm_op is not None
         g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_fb, capture_error_mode="relaxed"):
+        cap_stream = torch.cuda.Stream(self.flat.flat_p.device, priority=self._prio)
+        with torch.cuda.graph(g_fb, stream=cap_stream, capture_error_mode="relaxed"):
             self.static_loss, self.static_parts = self.forward_backward(self.static_pc, self.static_nor,
                                                                         self.static_eps, early=nccl_in_graph)
             if nccl_in_graph:
