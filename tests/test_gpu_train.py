@@ -116,7 +116,7 @@ def _c2_like(seed, streams):
     model = model.cuda()
     tr = T.DataParallelTrainer(model, lr=1e-3)
     if not streams:
-        tr.dw_stream = tr.res_stream = None
+        tr.dw_stream = tr.res_stream = tr.head_stream = None
     g = torch.Generator(device="cuda").manual_seed(seed)
     pc = torch.from_numpy(pts)[None].repeat(16, 1, 1).cuda() * 0.9 + torch.randn(16, len(pts), 3, device="cuda", generator=g) * 0.02
     nor = torch.from_numpy(synthetic.face_normals(pc.cpu().numpy(), faces)).float().cuda()
@@ -132,7 +132,7 @@ def test_parallel_branches_do_not_change_results():
     try:
         tr1, pc, nor = _c2_like(1, streams=False)
         tr2, _, _ = _c2_like(1, streams=True)
-        assert tr2.dw_stream is not None and tr2.res_stream is not None
+        assert tr2.dw_stream is not None and tr2.res_stream is not None and tr2.head_stream is not None
         eps = torch.randn(16, tr1.model.nrpt_latent, 64, device="cuda")
         for it in range(3):
             l1, _ = tr1.step(pc, nor, eps=eps)

@@ -399,6 +399,20 @@ def residual_stream():
     return _residual_stream
 
 
+# Optional stream for the second encoder head (mu and std share their input and stage 1; their basis GEMMs are a few
+# CTAs each and independent, forward and backward). Set by the trainer.
+_head_stream = None
+
+
+def set_head_stream(stream):
+    global _head_stream
+    _head_stream = stream
+
+
+def head_stream():
+    return _head_stream
+
+
 def join_side_stream():
     """The current stream waits for the branch; buffers parked for it are released."""
     for st in (_side_stream, _da_stream):

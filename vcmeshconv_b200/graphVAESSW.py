@@ -241,8 +241,27 @@ class MCEnc(nn.Module):
         head = self.layer_lst[last]
         # mu and std heads share input, table and coefficients: one gather/contract, two basis GEMMs
         z = F_.gather_contract(h, vcoeffs.vcoeffs_list[last], head.tables(h.device))
-        return (head.forward_from_z(z, h, is_final_layer=True),
-                self.stdlayer.forward_from_z(z, h, is_final_layer=True))
+        side = F_.head_stream() if h.is_cuda else None
+        if side is None:
+            return (head.forward_from_z(z, h, is_final_layer=True),
+                    self.stdlayer.forward_from_z(z, h, is_final_layer=True))
+        # the two heads are independent from here on (51 vertices: a few CTAs per kernel): run them side by side;
+        # autograd replays each head's backward on the stream of its forward
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        # The std head keeps its residual projection on its own stream: a residual tensor made on the shared residual
+        # stream dies as soon as this head's GEMM is enqueued, and the mu head's residual - ordered after `cur` only -
+        # would be handed the same memory while that GEMM may still be reading it.
+        res_stream = F_.residual_stream()
+        F_.set_residual_stream(None)
+        try:
+            with torch.cuda.stream(side):
+                std = self.stdlayer.forward_from_z(z, h, is_final_layer=True)
+        finally:
+            F_.set_residual_stream(res_stream)
+        mu = head.forward_from_z(z, h, is_final_layer=True)
+        cur.wait_stream(side)
+        return mu, std
 
     def forward(self, in_pc, vcoeffs):
         mu, std = self.forward_raw(in_pc, vcoeffs)

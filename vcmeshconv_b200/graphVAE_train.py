@@ -257,6 +257,9 @@ class DataParallelTrainer:
         self._prio = -1 if os.environ.get("VCM_STREAM_PRIO", "1") == "1" else 0
         self.res_stream = (torch.cuda.Stream(self.flat.flat_p.device, priority=self._prio)
                            if self.flat.flat_p.is_cuda and os.environ.get("VCM_RES_STREAM", "1") == "1" else None)
+        # the std head of the encoder next to the mu head (forward and backward); VCM_HEAD_STREAM=0 turns it off
+        self.head_stream = (torch.cuda.Stream(self.flat.flat_p.device, priority=self._prio)
+                            if self.flat.flat_p.is_cuda and os.environ.get("VCM_HEAD_STREAM", "1") == "1" else None)
         # decoder-side all-reduce + Adam next to the encoder's backward pass (VCM_EARLY_UPDATE=0 turns it off)
         self.early_stream = (torch.cuda.Stream(self.flat.flat_p.device)
                              if self.flat.flat_p.is_cuda and os.environ.get("VCM_EARLY_UPDATE", "1") == "1" else None)
@@ -427,6 +430,8 @@ class DataParallelTrainer:
                 self.model.net_geoenc.activation_hooks = {self._enc_hook_layer: lambda grad: self._segment_done(1)}
         if self.res_stream is not None and not self.overlap:
             F_.set_residual_stream(self.res_stream)
+        if self.head_stream is not None and not self.overlap:
+            F_.set_head_stream(self.head_stream)
         if self.prep_stream is not None:
             self.prep_stream.wait_stream(cur)
             F_.set_prep_stream(self.prep_stream)
@@ -434,6 +439,7 @@ class DataParallelTrainer:
             loss, l1, lap, kl, lnor, _ = self.model.losses(pc, nor, eps)
         finally:
             F_.set_residual_stream(None)
+            F_.set_head_stream(None)
             F_.set_prep_stream(None)
             if self.prep_stream is not None:
                 cur.wait_stream(self.prep_stream)
@@ -448,6 +454,8 @@ class DataParallelTrainer:
             F_.set_da_stream(None)
             if self.res_stream is not None and cur is not None:
                 cur.wait_stream(self.res_stream)     # residual-branch backward kernels (p_neighbors / weight_res grads)
+            if self.head_stream is not None and cur is not None:
+                cur.wait_stream(self.head_stream)    # the std head's backward kernels
             self._set_direct_grads(False)
             if getattr(self.model, "latent_grad_hook", None) is not None:
                 self.model.latent_grad_hook = None
@@ -464,7 +472,7 @@ class DataParallelTrainer:
         s = self.early_stream
         s.wait_stream(torch.cuda.current_stream())
         capturing = torch.cuda.is_current_stream_capturing()
-        for st in (F_._side_stream, F_._da_stream, self.res_stream):
+        for st in (F_._side_stream, F_._da_stream, self.res_stream, self.head_stream):
             if st is None:
                 continue
             if capturing:
