@@ -300,7 +300,6 @@ def _basis_backward(z, W, y, dout, cfg, need, dW_target, db_target, Wt=None):
         return (torch.zeros_like(z), torch.zeros_like(W),
                 (torch.zeros(p_out, O, device=dev) if per_point else torch.zeros(O, device=dev)) if need_db else None,
                 torch.zeros_like(dout) if need_dres else None)
-    ds = torch.empty_like(dout)
     direct_db = need_db and db_target is not None
     db_pp = None
     if need_db:
@@ -308,9 +307,13 @@ def _basis_backward(z, W, y, dout, cfg, need, dW_target, db_target, Wt=None):
     dres = torch.empty_like(dout) if need_dres else None
     ny = dout.numel()
     tag = "R%d K%d O%d" % (B * p_out, K, O)
-    _lib.call("vcm_act_bwd", _ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st,
-              nbytes=4 * (ny * (2 + (1 if act else 0) + (1 if need_dres else 0)) + (p_out * O if need_db else 0)),
-              flops=2 * ny, tag=tag)
+    if not act and sy == 1.0 and not need_db and not need_dres:
+        ds = dout                                # plain projection (residual 1x1, project-first bases): ds is dout itself
+    else:
+        ds = torch.empty_like(dout)
+        _lib.call("vcm_act_bwd", _ptr(dout), _ptr(y), _ptr(ds), _ptr(db_pp), _ptr(dres), B, p_out, O, act, sy, sr, st,
+                  nbytes=4 * (ny * (2 + (1 if act else 0) + (1 if need_dres else 0)) + (p_out * O if need_db else 0)),
+                  flops=2 * ny, tag=tag)
     dbias = None
     if need_db:
         if per_point:
