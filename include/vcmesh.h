@@ -151,6 +151,16 @@ VCM_API int vcm_coeff_grad_variant(const vcm_tables *t, int B, int I, int M, int
  * the 3-channel input layer and the M = 1 residual paths over xyz), otherwise the value above. */
 VCM_API int vcm_coeff_grad_variant_ex(const vcm_tables *t, int B, int I, int M, int precision, int want_dA,
                                       int want_dG);
+/* K5 with the final reduction taken off the backward chain. When the TMA kernel splits a vertex's units over several
+ * CTAs (few vertices: the coarse levels), every CTA row leaves one partial slab of dA [P_out,N,M] and a small kernel
+ * adds the slabs in fixed order. Only dG feeds the next kernel of the chain (K6); vcm_coeff_grad_slabs returns the
+ * number of slabs (0 = this shape does not split or is not served by that kernel), vcm_coeff_grad_slabs_launch runs
+ * K5 and leaves `slabs` [n_slabs][P_out*N*M] (the vcm_coeff_grad_workspace_ex size) unreduced, and vcm_sum_slabs -
+ * launched by the caller on a side stream - adds them: out[i] = slabs[0][i] + slabs[1][i] + ... in that order. */
+VCM_API int vcm_coeff_grad_slabs(const vcm_tables *t, int B, int I, int M, int precision);
+VCM_API int vcm_coeff_grad_slabs_launch(const vcm_tables *t, const float *dz, const float *x, const float *A,
+                                        float *slabs, float *dG, int B, int I, int M, int precision, void *stream);
+VCM_API int vcm_sum_slabs(const float *slabs, float *out, size_t n, int n_slabs, void *stream);
 VCM_API size_t vcm_coeff_grad_workspace_ex(const vcm_tables *t, int B, int I, int M, int precision);
 VCM_API int vcm_coeff_grad_ex(const vcm_tables *t, const float *dz, const float *x, const float *A, float *dA,
                               float *dG, float *workspace, int B, int I, int M, int precision, void *stream);

@@ -42,6 +42,9 @@ SIGNATURES = {
     "vcm_coeff_grad": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vcm_coeff_grad_variant": (_i, [_p, _i, _i, _i, _i]),
     "vcm_coeff_grad_variant_ex": (_i, [_p, _i, _i, _i, _i, _i, _i]),
+    "vcm_coeff_grad_slabs": (_i, [_p, _i, _i, _i, _i]),
+    "vcm_coeff_grad_slabs_launch": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "vcm_sum_slabs": (_i, [_p, _p, _sz, _i, _p]),
     "vcm_coeff_grad_workspace_ex": (_sz, [_p, _i, _i, _i, _i]),
     "vcm_coeff_grad_ex": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "vcm_scatter_rev": (_i, [_p, _p, _p, _i, _i, _i, _p]),

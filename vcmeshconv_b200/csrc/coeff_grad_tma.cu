@@ -522,7 +522,7 @@ size_t k5_tma_workspace(const Tables *t, const K5TmaPlan &pl, int M) {
 }
 
 int k5_tma_launch(const Tables *t, const K5TmaPlan &pl, const float *dz, const float *x, const float *A, float *dA,
-                  float *dG, float *ws, int B, int I, int M, cudaStream_t st) {
+                  float *dG, float *ws, int B, int I, int M, cudaStream_t st, bool defer_sum) {
     if (dA != nullptr && pl.gy > 1 && ws == nullptr) return fail(VCM_EINVAL, "workspace required (%d splits)", pl.gy);
     if (!aligned16(dz) || !aligned16(x) || (dG && !aligned16(dG))) return fail(VCM_EINVAL, "dz, x and dG must be 16-byte aligned");
     CUtensorMap map;
@@ -544,7 +544,7 @@ int k5_tma_launch(const Tables *t, const K5TmaPlan &pl, const float *dz, const f
     P.stage_bytes = P.x_off = P.zero_off = 0;
     int e = pl.cw == 64 ? launch_cw<64>(map, t, pl, P, M, st) : launch_cw<32>(map, t, pl, P, M, st);
     if (e) return e;
-    if (dA != nullptr && pl.gy > 1) launch_sum_splits(ws, dA, (size_t)t->p_out * t->n_max * M, pl.gy, st);
+    if (dA != nullptr && pl.gy > 1 && !defer_sum) launch_sum_splits(ws, dA, (size_t)t->p_out * t->n_max * M, pl.gy, st);
     return VCM_OK;
 }
 

@@ -1533,6 +1533,37 @@ int vcm_coeff_grad_variant(const vcm_tables *h, int B, int I, int M, int precisi
     return use_grad_mma(vcm::as_tables(h), B, I, M, precision, &pl) ? 1 : 0;
 }
 
+int vcm_coeff_grad_slabs(const vcm_tables *h, int B, int I, int M, int precision) {
+    using namespace vcm;
+    const Tables *t = as_tables(h);
+    K5TmaPlan tp;
+    if (t == nullptr || k5_small_ok(t, B, I, M, precision, true, true) || !k5_tma_plan(t, B, I, M, precision, &tp)) return 0;
+    return tp.gy > 1 ? tp.gy : 0;
+}
+
+int vcm_coeff_grad_slabs_launch(const vcm_tables *h, const float *dz, const float *x, const float *A, float *slabs,
+                                float *dG, int B, int I, int M, int precision, void *stream) {
+    using namespace vcm;
+    const Tables *t = as_tables(h);
+    K5TmaPlan tp;
+    VCM_CHECK(vcm_coeff_grad_slabs(h, B, I, M, precision) > 1 && k5_tma_plan(t, B, I, M, precision, &tp),
+              "this shape leaves no partial slabs (query vcm_coeff_grad_slabs)");
+    VCM_DEVPTR(dz); VCM_DEVPTR(x); VCM_DEVPTR(A); VCM_DEVPTR(slabs); VCM_DEVPTR_OPT(dG);
+    if (int e0 = check_common(t, B, I, M)) return e0;
+    // the first slab pointer doubles as the (unused) final destination
+    return k5_tma_launch(t, tp, dz, x, A, slabs, dG, slabs, B, I, M, (cudaStream_t)stream, true);
+}
+
+int vcm_sum_slabs(const float *slabs, float *out, size_t n, int n_slabs, void *stream) {
+    VCM_CHECK(n_slabs >= 1, "bad slab count %d", n_slabs);
+    VCM_DEVPTR(slabs); VCM_DEVPTR(out);
+    if (n == 0) return VCM_OK;
+    vcm::launch_sum_splits(slabs, out, n, n_slabs, (cudaStream_t)stream);        // counts its launch
+    const cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return vcm::fail((int)e, "kernel launch failed: %s", cudaGetErrorString(e));
+    return VCM_OK;
+}
+
 int vcm_coeff_grad_ex(const vcm_tables *h, const float *dz, const float *x, const float *A, float *dA, float *dG,
                       float *ws, int B, int I, int M, int precision, void *stream) {
     using namespace vcm;

@@ -17,7 +17,8 @@ struct K5TmaPlan {
 bool k5_tma_plan(const Tables *t, int B, int I, int M, int precision, K5TmaPlan *pl);
 size_t k5_tma_workspace(const Tables *t, const K5TmaPlan &pl, int M);
 int k5_tma_launch(const Tables *t, const K5TmaPlan &pl, const float *dz, const float *x, const float *A, float *dA,
-                  float *dG, float *ws, int B, int I, int M, cudaStream_t st);
+                  float *dG, float *ws, int B, int I, int M, cudaStream_t st, bool defer_sum = false);
+// defer_sum: with gy > 1 leave the gy partial slabs of dA in the workspace (the caller sums them off the chain)
 
 // sums `n_split` slabs of n floats in fixed order (gather.cu)
 void launch_sum_splits(const float *part, float *out, size_t n, int n_split, cudaStream_t st);

@@ -113,6 +113,9 @@ class _GatherContract(torch.autograd.Function):
         return dx, dA, None
 
 
+_defer_slab_sum = __import__("os").environ.get("VCM_DEFER_SLAB_SUM", "1") == "1"
+
+
 def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
     """K5 (+ K6): (dx, dA) of z = gather_contract(x, A); dA is None when it was written into `dA_target`."""
     B, p_in, I = x.shape
@@ -161,6 +164,20 @@ def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
                       precision, _lib.stream_ptr(), nbytes=4 * (dz.numel() + x.numel() + 2 * nnz * M + nnz),
                       flops=2 * B * nnz * M * I, tag=tag)
         _side_keep.append((dz, x, ws))
+    elif (need_dx and direct_dA and _side_stream is not None and _defer_slab_sum
+          and L.vcm_coeff_grad_slabs(t.handle, B, I, M, precision) > 1):
+        # few vertices: K5 leaves one partial slab of dA per CTA row. Only dG continues down the chain (K6), so the
+        # fixed-order sum of the slabs into the flat gradient buffer runs on the side stream next to it.
+        n_slabs = L.vcm_coeff_grad_slabs(t.handle, B, I, M, precision)
+        _lib.call("vcm_coeff_grad_slabs_launch", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(ws), _ptr(dG), B, I, M,
+                  precision, st,
+                  nbytes=4 * (dz.numel() + x.numel() + 2 * nnz * M + nnz) + gb,
+                  flops=4 * B * nnz * M * I, tag=tag)
+        _side_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(_side_stream):
+            _lib.call("vcm_sum_slabs", _ptr(ws), _ptr(dA), dA.numel(), n_slabs, _lib.stream_ptr(),
+                      nbytes=4 * dA.numel() * (n_slabs + 1), flops=dA.numel() * n_slabs, tag=tag)
+        _side_keep.append((ws,))
     else:
         _lib.call("vcm_coeff_grad_ex", t.handle, _ptr(dz), _ptr(x), _ptr(A), _ptr(dA), _ptr(dG), _ptr(ws), B, I, M,
                   precision, st,

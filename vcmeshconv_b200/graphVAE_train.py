@@ -417,7 +417,15 @@ class DataParallelTrainer:
         of the flat buffers is all-reduced and its Adam update applied on `early_stream` as soon as the decoder's
         backward pass is complete, next to the encoder's backward pass; the caller finishes the step with
         _finish_reduction() + optimizer_step(), which then only touch the rest."""
-        self.flat.zero_grad()
+        cur = torch.cuda.current_stream() if self.flat.flat_p.is_cuda else None
+        if self.prep_stream is not None:
+            # nothing reads or writes the gradient buffer before the backward pass: clear it next to the forward pass
+            # (the preparation stream is joined before backward starts)
+            self.prep_stream.wait_stream(cur)
+            with torch.cuda.stream(self.prep_stream):
+                self.flat.zero_grad()
+        else:
+            self.flat.zero_grad()
         # direct gradient writes (backward kernels fill the flat buffer in place, OVERWRITING it) are enabled for the
         # duration of this call only: a backward() the user runs outside goes through ordinary autograd accumulation
         self._set_direct_grads(self._direct)
