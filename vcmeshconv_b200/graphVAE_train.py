@@ -264,7 +264,8 @@ class DataParallelTrainer:
         self.head_stream = (torch.cuda.Stream(self.flat.flat_p.device, priority=self._prio)
                             if self.flat.flat_p.is_cuda and os.environ.get("VCM_HEAD_STREAM", "1") == "1" else None)
         # decoder-side all-reduce + Adam next to the encoder's backward pass (VCM_EARLY_UPDATE=0 turns it off)
-        self.early_stream = (torch.cuda.Stream(self.flat.flat_p.device)
+        self.early_stream = (torch.cuda.Stream(self.flat.flat_p.device,
+                                               priority=int(os.environ.get("VCM_PRIO_EARLY", "0")))
                              if self.flat.flat_p.is_cuda and os.environ.get("VCM_EARLY_UPDATE", "1") == "1" else None)
         self._advanced = self._early_done = False
         self._early_upto = 0
