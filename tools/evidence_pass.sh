@@ -1,3 +1,7 @@
+#!/bin/bash
+# One-GPU evidence pass of a round: GPU tests, the bench line of every single-GPU config with its breakdown, the
+# 2000-step line, the graph timeline and the ncu launch list (after the same command exited 0 without ncu).
+# Everything lands in gpurun_out/ev/; copy what should be judged into profiles/.
 set -u
 o=gpurun_out/ev
 mkdir -p $o
@@ -13,4 +17,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 cat $o/pytest_gpu.txt; for c in c2 c1 c5 c3 c2_steps2000; do python -c "
 import json,sys
 d=json.loads(open('$o/bench_$c.json').read().strip().splitlines()[-1])
-print('$c', d['value'], d['ms_per_step'], d.get('e2e',{}).get('value'), d.get('roofline',{}).get('kernel'), d.get('roofline',{}).get('frac'), d.get('clocks'))"; done
+print('$c', d['value'], d['ms_per_step'], d.get('e2e',{}).get('value'), (d.get('roofline') or {}).get('kernel'), (d.get('roofline') or {}).get('frac'), d.get('clocks'))"; done

@@ -114,6 +114,9 @@ class _GatherContract(torch.autograd.Function):
 
 
 _defer_slab_sum = __import__("os").environ.get("VCM_DEFER_SLAB_SUM", "1") == "1"
+# VCM_SPLIT_K5=1 (trainer): the dA half of K5 as a parallel branch, for layers whose dz is at most this many MB (the
+# split reads dz twice: it can only pay where K5 is latency-bound, not on the layers that carry the bytes)
+_split_k5_max_bytes = int(float(__import__("os").environ.get("VCM_SPLIT_K5_MAX_MB", "1e9")) * (1 << 20))
 
 
 def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
@@ -141,7 +144,7 @@ def _gather_backward(t, x, A, dz, need_dx, need_dA, dA_target, precision):
     dA = (dA_target if direct_dA else torch.empty_like(A)) if need_dA else None
     dG = torch.empty(B, t.p_out, t.n_max, I, device=x.device, dtype=torch.float32) if need_dx else None
     n_ws = L.vcm_coeff_grad_workspace_ex(t.handle, B, I, M, precision) if need_dA else 0
-    split = need_dx and direct_dA and _da_stream is not None
+    split = need_dx and direct_dA and _da_stream is not None and 4 * dz.numel() <= _split_k5_max_bytes
     ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws and not split else None
     st = _lib.stream_ptr()
     nnz = t.nnz
